@@ -1,0 +1,127 @@
+/* fcsearch.h -- C ABI of the B200-native Foldclass database search.
+ *
+ * Drop-in boundary for the search hot path of psipred/merizo_search.  The
+ * reference has no FFI of its own (it is pure Python); the three Python callables
+ * this library sits behind are (paths relative to merizo_search/programs/Foldclass/):
+ *
+ *   read_database()            dbsearch.py:48-72   -> fcs_db_create / fcs_db_upload* / fcs_db_finalize
+ *   search_query_against_db()  dbsearch.py:75-81   -> fcs_search (qnorm = FCS_QNORM_COSINE, lengths + mincov)
+ *   knn_exact_faiss()          dbsearch.py:213-248 -> fcs_search (qnorm = FCS_QNORM_NONE / FCS_QNORM_L2, no mask)
+ *   F.normalize(queries)       dbsearch.py:303-304 -> qnorm = FCS_QNORM_L2 (fused into the search kernels)
+ *   db_memmap()/db_iterator()  dbutil.py:28-35     -> the host feeds fcs_db_upload block by block, ONCE
+ *
+ * Plain pointers and sizes only; no torch types.  Every function returns FCS_OK (0)
+ * or a negative error code and never throws or exits; the message of the last error
+ * on the calling thread is available from fcs_last_error().
+ *
+ * A handle owns ONE row shard on ONE device (global ids = id_offset + local row).
+ * Multi-GPU = one handle per GPU (one per rank under torchrun, or several handles in
+ * one process) plus fcs_merge_topk over the gathered per-shard key lists.
+ */
+#ifndef FCSEARCH_H
+#define FCSEARCH_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FCS_DIM 128 /* embedding width: FoldClassNet(128), dbsearch.py:39 */
+
+/* error codes */
+#define FCS_OK 0
+#define FCS_ERR_INVALID (-1)     /* bad argument */
+#define FCS_ERR_CUDA (-2)        /* CUDA runtime/driver error (message has the detail) */
+#define FCS_ERR_STATE (-3)       /* call sequence error (e.g. search before finalize) */
+#define FCS_ERR_UNSUPPORTED (-4) /* k / mode outside what the kernels implement */
+#define FCS_ERR_NOMEM (-5)       /* device or pinned host allocation failed */
+
+/* fcs_db_create flags */
+#define FCS_DB_NORMALISE_ROWS 1u /* .pt flavour: rows are raw; divide each by max(|row|,1e-8)
+                                    (F.cosine_similarity semantics, dbsearch.py:78)            */
+#define FCS_DB_KEEP_BF16 2u      /* keep a bf16 copy of the (normalised) rows for the tcgen05 path */
+#define FCS_DB_HAS_LENGTHS 4u    /* per-row domain lengths are uploaded (coverage mask, dbsearch.py:76) */
+
+/* query normalisation, fused into the search kernels */
+#define FCS_QNORM_NONE 0   /* use queries as given (already normalised) */
+#define FCS_QNORM_COSINE 1 /* q / max(|q|, 1e-8)   -- F.cosine_similarity, dbsearch.py:78 */
+#define FCS_QNORM_L2 2     /* q / max(|q|, 1e-12)  -- F.normalize,          dbsearch.py:304 */
+
+/* search mode */
+#define FCS_MODE_AUTO 0 /* GEMV for small batches, tensor-core path for large ones when a bf16 copy exists */
+#define FCS_MODE_GEMV 1 /* exact fp32 streaming kernel (HBM-bound) */
+#define FCS_MODE_TC 2   /* bf16 tcgen05 GEMM + fused top-k' + exact fp32 rescore (needs FCS_DB_KEEP_BF16) */
+
+#define FCS_MAX_K 2048 /* like faiss-gpu's k-selection limit */
+
+typedef struct fcs_db fcs_db;
+
+typedef struct fcs_timing {
+    float last_search_ms;     /* device time of the last fcs_search* call (CUDA events on the handle's stream) */
+    float last_kernel_ms;     /* device time of the dominant kernel(s) of that call */
+    int32_t last_mode;        /* FCS_MODE_GEMV or FCS_MODE_TC actually used */
+    int32_t last_launches;    /* kernels launched by that call */
+    int32_t last_tc_fallbacks; /* TC path: queries whose exactness certificate failed and were re-run on the GEMV path */
+    int32_t reserved;
+} fcs_timing;
+
+typedef struct fcs_info {
+    int64_t n_rows;
+    int64_t id_offset;
+    int32_t device;
+    uint32_t flags;
+    int32_t finalized;
+    int32_t sm_count;
+    uint64_t bytes_fp32;
+    uint64_t bytes_bf16;
+} fcs_info;
+
+/* library ------------------------------------------------------------------------- */
+int fcs_version(void);                 /* MAJOR*10000 + MINOR*100 + PATCH */
+const char* fcs_last_error(void);      /* thread-local; "" if none */
+int fcs_device_count(int* out_count);  /* FCS_ERR_CUDA if there is no usable GPU */
+
+/* database handle (replaces read_database, dbsearch.py:48-72) -------------------- */
+int fcs_db_create(int device, int64_t n_rows, int dim /* must be 128 */, int64_t id_offset,
+                  uint32_t flags, fcs_db** out);
+/* Copy rows [row0, row0+n) from HOST memory (pageable is fine: staged through pinned
+ * buffers).  lengths (int32, one per row) is required iff FCS_DB_HAS_LENGTHS. */
+int fcs_db_upload(fcs_db* db, int64_t row0, int64_t n, const float* host_rows, const int32_t* host_lengths);
+/* Same, from DEVICE memory on the handle's device (synthetic DBs, torch CUDA tensors). */
+int fcs_db_upload_device(fcs_db* db, int64_t row0, int64_t n, const float* dev_rows, const int32_t* dev_lengths);
+/* Normalise rows (if asked), build the bf16 copy (if asked), allocate search scratch. */
+int fcs_db_finalize(fcs_db* db);
+int fcs_db_get_info(const fcs_db* db, fcs_info* out);
+int fcs_db_destroy(fcs_db* db);
+
+/* search (replaces search_query_against_db dbsearch.py:75-81 and knn_exact_faiss
+ * dbsearch.py:213-248) -------------------------------------------------------------
+ *   q          [nq,128] fp32 row-major, HOST memory
+ *   qlen       per-query residue count (len(query_dict['seq'])) or NULL = no coverage mask
+ *   mincov     coverage threshold (only used when qlen != NULL and the db has lengths)
+ *   k          1..FCS_MAX_K.  Slots beyond the number of rows hold (-inf, -1) (faiss convention)
+ *   kprime     TC path: candidates kept per query before the fp32 rescore; 0 = default
+ *   out_scores [nq,k] fp32, out_ids [nq,k] int64 (global ids), HOST memory, sorted by
+ *              descending score (ties: ascending id).  Fully written on return. */
+int fcs_search(fcs_db* db, const float* q, int nq, const int32_t* qlen, float mincov, int k, int qnorm,
+               int mode, int kprime, float* out_scores, int64_t* out_ids);
+/* Same with DEVICE buffers, asynchronous on `stream` (a cudaStream_t; NULL = the
+ * handle's own stream).  qlen stays a HOST array.  out_keys ([nq,k] uint64, optional)
+ * receives the packed sort keys that fcs_merge_topk consumes. */
+int fcs_search_device(fcs_db* db, const float* q_dev, int nq, const int32_t* qlen, float mincov, int k,
+                      int qnorm, int mode, int kprime, float* out_scores_dev, int64_t* out_ids_dev,
+                      uint64_t* out_keys_dev, void* stream);
+
+/* cross-shard merge (replaces faiss.ResultHeap.add_result/finalize, dbsearch.py:224-245):
+ *   keys_dev [n_lists][nq][k] packed keys from fcs_search_device of each shard (after the
+ *   all-gather), -> the k best per query, decoded.  Asynchronous on `stream`. */
+int fcs_merge_topk(int device, const uint64_t* keys_dev, int n_lists, int nq, int k, float* out_scores_dev,
+                   int64_t* out_ids_dev, void* stream);
+
+int fcs_get_timing(const fcs_db* db, fcs_timing* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FCSEARCH_H */

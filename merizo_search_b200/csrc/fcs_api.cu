@@ -1,0 +1,484 @@
+// fcs_api.cu -- the C ABI declared in include/fcsearch.h: handle, loader, search dispatch.
+// No torch types, no exceptions across the boundary, no exit(): errors are codes + fcs_last_error().
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "fcs_common.cuh"
+#include "fcs_internal.h"
+#include "fcs_tc.h"
+
+using namespace fcs;
+
+// ------------------------------------------------------------------------------------ errors
+static thread_local std::string g_last_error;
+
+static int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+#define FCS_CUDA(call)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t e__ = (call);                                                                        \
+        if (e__ != cudaSuccess) {                                                                        \
+            const int code__ = (e__ == cudaErrorMemoryAllocation) ? FCS_ERR_NOMEM : FCS_ERR_CUDA;        \
+            (void)cudaGetLastError();                                                                    \
+            return fail(code__, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+        }                                                                                                \
+    } while (0)
+
+namespace {
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        ok = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+constexpr size_t STAGE_BYTES_HOST = size_t(32) << 20;  // pinned staging buffers for fcs_db_upload
+}  // namespace
+
+// ------------------------------------------------------------------------------------ handle
+struct fcs_db {
+    int device = 0;
+    int64_t n_rows = 0;
+    int64_t id_offset = 0;
+    uint32_t flags = 0;
+    bool finalized = false;
+    int sm_count = 0;
+    int64_t uploaded_rows = 0;
+
+    float* rows = nullptr;         // [n_rows,128] fp32
+    void* rows_bf16 = nullptr;     // [n_rows,128] bf16 (optional)
+    uint16_t* lens = nullptr;      // [n_rows] (optional)
+
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool ev_valid = false;
+
+    uint64_t* gemv_scratch = nullptr;
+    unsigned* ticket = nullptr;
+    int* d_bad = nullptr;
+
+    // buffers behind the host-pointer API (grown on demand)
+    float* d_q = nullptr;
+    size_t d_q_cap = 0;  // queries
+    uint64_t* d_keys = nullptr;
+    float* d_scores = nullptr;
+    int64_t* d_ids = nullptr;
+    size_t d_out_cap = 0;  // entries
+    float* h_q = nullptr;
+    size_t h_q_cap = 0;
+    float* h_scores = nullptr;
+    int64_t* h_ids = nullptr;
+    size_t h_out_cap = 0;
+
+    void* h_stage[2] = {nullptr, nullptr};
+    cudaEvent_t stage_ev[2] = {nullptr, nullptr};
+    int stage_next = 0;
+
+    TcState* tc = nullptr;
+    fcs_timing timing = {};
+};
+
+static int ensure_query_bufs(fcs_db* db, size_t nq, bool host) {
+    if (db->d_q_cap < nq) {
+        if (db->d_q) cudaFree(db->d_q);
+        db->d_q = nullptr;
+        db->d_q_cap = 0;
+        FCS_CUDA(cudaMalloc(&db->d_q, nq * DIM * sizeof(float)));
+        db->d_q_cap = nq;
+    }
+    if (host && db->h_q_cap < nq) {
+        if (db->h_q) cudaFreeHost(db->h_q);
+        db->h_q = nullptr;
+        db->h_q_cap = 0;
+        FCS_CUDA(cudaMallocHost(&db->h_q, nq * DIM * sizeof(float)));
+        db->h_q_cap = nq;
+    }
+    return FCS_OK;
+}
+
+static int ensure_out_bufs(fcs_db* db, size_t entries, bool host) {
+    if (db->d_out_cap < entries) {
+        if (db->d_keys) cudaFree(db->d_keys);
+        if (db->d_scores) cudaFree(db->d_scores);
+        if (db->d_ids) cudaFree(db->d_ids);
+        db->d_keys = nullptr; db->d_scores = nullptr; db->d_ids = nullptr;
+        db->d_out_cap = 0;
+        FCS_CUDA(cudaMalloc(&db->d_keys, entries * sizeof(uint64_t)));
+        FCS_CUDA(cudaMalloc(&db->d_scores, entries * sizeof(float)));
+        FCS_CUDA(cudaMalloc(&db->d_ids, entries * sizeof(int64_t)));
+        db->d_out_cap = entries;
+    }
+    if (host && db->h_out_cap < entries) {
+        if (db->h_scores) cudaFreeHost(db->h_scores);
+        if (db->h_ids) cudaFreeHost(db->h_ids);
+        db->h_scores = nullptr; db->h_ids = nullptr;
+        db->h_out_cap = 0;
+        FCS_CUDA(cudaMallocHost(&db->h_scores, entries * sizeof(float)));
+        FCS_CUDA(cudaMallocHost(&db->h_ids, entries * sizeof(int64_t)));
+        db->h_out_cap = entries;
+    }
+    return FCS_OK;
+}
+
+// ------------------------------------------------------------------------------------ library
+extern "C" int fcs_version(void) { return 100; }
+extern "C" const char* fcs_last_error(void) { return g_last_error.c_str(); }
+
+extern "C" int fcs_device_count(int* out_count) {
+    if (!out_count) return fail(FCS_ERR_INVALID, "fcs_device_count: out_count is NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        *out_count = 0;
+        return fail(FCS_ERR_CUDA, "cudaGetDeviceCount failed: %s", cudaGetErrorString(e));
+    }
+    *out_count = n;
+    return FCS_OK;
+}
+
+// ------------------------------------------------------------------------------------ create / destroy
+extern "C" int fcs_db_create(int device, int64_t n_rows, int dim, int64_t id_offset, uint32_t flags, fcs_db** out) {
+    if (!out) return fail(FCS_ERR_INVALID, "fcs_db_create: out is NULL");
+    *out = nullptr;
+    if (dim != DIM) return fail(FCS_ERR_INVALID, "fcs_db_create: dim must be %d (got %d)", DIM, dim);
+    if (n_rows < 1) return fail(FCS_ERR_INVALID, "fcs_db_create: n_rows must be >= 1 (got %lld)", (long long)n_rows);
+    if (id_offset < 0 || id_offset + n_rows >= int64_t(0xFFFFFFFFll))
+        return fail(FCS_ERR_INVALID, "fcs_db_create: global ids must stay below 2^32-1 (offset %lld + rows %lld)",
+                    (long long)id_offset, (long long)n_rows);
+    if (flags & ~(FCS_DB_NORMALISE_ROWS | FCS_DB_KEEP_BF16 | FCS_DB_HAS_LENGTHS))
+        return fail(FCS_ERR_INVALID, "fcs_db_create: unknown flag bits 0x%x", flags);
+    int ndev = 0;
+    FCS_CUDA(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(FCS_ERR_INVALID, "fcs_db_create: device %d out of range (%d GPUs)", device, ndev);
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(FCS_ERR_CUDA, "fcs_db_create: cudaSetDevice(%d) failed", device);
+    cudaDeviceProp prop;
+    FCS_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(FCS_ERR_UNSUPPORTED, "fcs_db_create: device %d is sm_%d%d; this library is built for sm_100a only", device,
+                    prop.major, prop.minor);
+    fcs_db* db = new (std::nothrow) fcs_db();
+    if (!db) return fail(FCS_ERR_NOMEM, "fcs_db_create: out of host memory");
+    db->device = device;
+    db->n_rows = n_rows;
+    db->id_offset = id_offset;
+    db->flags = flags;
+    db->sm_count = prop.multiProcessorCount;
+    int rc = FCS_OK;
+    auto run = [&]() -> int {
+        FCS_CUDA(gemv_configure());
+        FCS_CUDA(cudaStreamCreateWithFlags(&db->stream, cudaStreamNonBlocking));
+        FCS_CUDA(cudaEventCreate(&db->ev0));
+        FCS_CUDA(cudaEventCreate(&db->ev1));
+        FCS_CUDA(cudaMalloc(&db->rows, size_t(n_rows) * ROW_BYTES));
+        if (flags & FCS_DB_HAS_LENGTHS) FCS_CUDA(cudaMalloc(&db->lens, size_t(n_rows) * sizeof(uint16_t)));
+        if (flags & FCS_DB_KEEP_BF16) FCS_CUDA(cudaMalloc(&db->rows_bf16, size_t(n_rows) * DIM * 2));
+        FCS_CUDA(cudaMalloc(&db->gemv_scratch, gemv_scratch_bytes(db->sm_count)));
+        FCS_CUDA(cudaMalloc(&db->ticket, sizeof(unsigned)));
+        FCS_CUDA(cudaMemsetAsync(db->ticket, 0, sizeof(unsigned), db->stream));
+        FCS_CUDA(cudaMalloc(&db->d_bad, sizeof(int)));
+        FCS_CUDA(cudaMemsetAsync(db->d_bad, 0, sizeof(int), db->stream));
+        FCS_CUDA(cudaStreamSynchronize(db->stream));
+        return FCS_OK;
+    };
+    rc = run();
+    if (rc != FCS_OK) {
+        std::string keep = g_last_error;
+        fcs_db_destroy(db);
+        g_last_error = keep;
+        return rc;
+    }
+    *out = db;
+    return FCS_OK;
+}
+
+extern "C" int fcs_db_destroy(fcs_db* db) {
+    if (!db) return FCS_OK;
+    DeviceGuard guard(db->device);
+    if (db->stream) cudaStreamSynchronize(db->stream);
+    if (db->tc) tc_destroy(db->tc);
+    cudaFree(db->rows);
+    cudaFree(db->rows_bf16);
+    cudaFree(db->lens);
+    cudaFree(db->gemv_scratch);
+    cudaFree(db->ticket);
+    cudaFree(db->d_bad);
+    cudaFree(db->d_q);
+    cudaFree(db->d_keys);
+    cudaFree(db->d_scores);
+    cudaFree(db->d_ids);
+    if (db->h_q) cudaFreeHost(db->h_q);
+    if (db->h_scores) cudaFreeHost(db->h_scores);
+    if (db->h_ids) cudaFreeHost(db->h_ids);
+    for (int i = 0; i < 2; ++i) {
+        if (db->h_stage[i]) cudaFreeHost(db->h_stage[i]);
+        if (db->stage_ev[i]) cudaEventDestroy(db->stage_ev[i]);
+    }
+    if (db->ev0) cudaEventDestroy(db->ev0);
+    if (db->ev1) cudaEventDestroy(db->ev1);
+    if (db->stream) cudaStreamDestroy(db->stream);
+    (void)cudaGetLastError();
+    delete db;
+    return FCS_OK;
+}
+
+extern "C" int fcs_db_get_info(const fcs_db* db, fcs_info* out) {
+    if (!db || !out) return fail(FCS_ERR_INVALID, "fcs_db_get_info: NULL argument");
+    out->n_rows = db->n_rows;
+    out->id_offset = db->id_offset;
+    out->device = db->device;
+    out->flags = db->flags;
+    out->finalized = db->finalized ? 1 : 0;
+    out->sm_count = db->sm_count;
+    out->bytes_fp32 = uint64_t(db->n_rows) * ROW_BYTES;
+    out->bytes_bf16 = db->rows_bf16 ? uint64_t(db->n_rows) * DIM * 2 : 0;
+    return FCS_OK;
+}
+
+// ------------------------------------------------------------------------------------ upload
+static int check_upload(fcs_db* db, int64_t row0, int64_t n, const void* rows, const void* lengths, const char* fn) {
+    if (!db) return fail(FCS_ERR_INVALID, "%s: db is NULL", fn);
+    if (db->finalized) return fail(FCS_ERR_STATE, "%s: database already finalized", fn);
+    if (!rows) return fail(FCS_ERR_INVALID, "%s: rows is NULL", fn);
+    if (row0 < 0 || n < 0 || row0 + n > db->n_rows)
+        return fail(FCS_ERR_INVALID, "%s: rows [%lld, %lld) outside [0, %lld)", fn, (long long)row0, (long long)(row0 + n),
+                    (long long)db->n_rows);
+    if ((db->flags & FCS_DB_HAS_LENGTHS) && !lengths) return fail(FCS_ERR_INVALID, "%s: lengths required (FCS_DB_HAS_LENGTHS)", fn);
+    return FCS_OK;
+}
+
+extern "C" int fcs_db_upload(fcs_db* db, int64_t row0, int64_t n, const float* host_rows, const int32_t* host_lengths) {
+    int rc = check_upload(db, row0, n, host_rows, host_lengths, "fcs_db_upload");
+    if (rc != FCS_OK) return rc;
+    if (n == 0) return FCS_OK;
+    DeviceGuard guard(db->device);
+    for (int i = 0; i < 2; ++i) {
+        if (!db->h_stage[i]) {
+            FCS_CUDA(cudaMallocHost(&db->h_stage[i], STAGE_BYTES_HOST));
+            FCS_CUDA(cudaEventCreateWithFlags(&db->stage_ev[i], cudaEventDisableTiming));
+        }
+    }
+    // rows: pageable -> pinned (CPU copy) -> device (async DMA), double-buffered
+    const int64_t rows_per_stage = int64_t(STAGE_BYTES_HOST / ROW_BYTES);
+    for (int64_t r = 0; r < n; r += rows_per_stage) {
+        const int64_t cnt = (n - r < rows_per_stage) ? (n - r) : rows_per_stage;
+        const int b = db->stage_next;
+        db->stage_next ^= 1;
+        FCS_CUDA(cudaEventSynchronize(db->stage_ev[b]));
+        memcpy(db->h_stage[b], host_rows + r * DIM, size_t(cnt) * ROW_BYTES);
+        FCS_CUDA(cudaMemcpyAsync(db->rows + (row0 + r) * DIM, db->h_stage[b], size_t(cnt) * ROW_BYTES, cudaMemcpyHostToDevice,
+                                 db->stream));
+        FCS_CUDA(cudaEventRecord(db->stage_ev[b], db->stream));
+    }
+    if (db->flags & FCS_DB_HAS_LENGTHS) {
+        const int64_t per_stage = int64_t(STAGE_BYTES_HOST / sizeof(uint16_t));
+        for (int64_t r = 0; r < n; r += per_stage) {
+            const int64_t cnt = (n - r < per_stage) ? (n - r) : per_stage;
+            const int b = db->stage_next;
+            db->stage_next ^= 1;
+            FCS_CUDA(cudaEventSynchronize(db->stage_ev[b]));
+            uint16_t* dst = static_cast<uint16_t*>(db->h_stage[b]);
+            for (int64_t i = 0; i < cnt; ++i) {
+                const int32_t v = host_lengths[r + i];
+                if (v < 0 || v > 65535)
+                    return fail(FCS_ERR_INVALID, "fcs_db_upload: length %d of row %lld outside [0, 65535]", v, (long long)(row0 + r + i));
+                dst[i] = uint16_t(v);
+            }
+            FCS_CUDA(cudaMemcpyAsync(db->lens + row0 + r, dst, size_t(cnt) * sizeof(uint16_t), cudaMemcpyHostToDevice, db->stream));
+            FCS_CUDA(cudaEventRecord(db->stage_ev[b], db->stream));
+        }
+    }
+    db->uploaded_rows += n;
+    return FCS_OK;
+}
+
+extern "C" int fcs_db_upload_device(fcs_db* db, int64_t row0, int64_t n, const float* dev_rows, const int32_t* dev_lengths) {
+    int rc = check_upload(db, row0, n, dev_rows, dev_lengths, "fcs_db_upload_device");
+    if (rc != FCS_OK) return rc;
+    if (n == 0) return FCS_OK;
+    DeviceGuard guard(db->device);
+    // the source may have been produced on another stream (e.g. torch's): make it visible first
+    FCS_CUDA(cudaDeviceSynchronize());
+    FCS_CUDA(cudaMemcpyAsync(db->rows + row0 * DIM, dev_rows, size_t(n) * ROW_BYTES, cudaMemcpyDeviceToDevice, db->stream));
+    if (db->flags & FCS_DB_HAS_LENGTHS)
+        FCS_CUDA(lengths_to_u16_launch(dev_lengths, db->lens + row0, n, db->d_bad, db->stream));
+    FCS_CUDA(cudaStreamSynchronize(db->stream));  // the caller may free dev_rows right after
+    db->uploaded_rows += n;
+    return FCS_OK;
+}
+
+extern "C" int fcs_db_finalize(fcs_db* db) {
+    if (!db) return fail(FCS_ERR_INVALID, "fcs_db_finalize: db is NULL");
+    if (db->finalized) return FCS_OK;
+    if (db->uploaded_rows < db->n_rows)
+        return fail(FCS_ERR_STATE, "fcs_db_finalize: only %lld of %lld rows uploaded", (long long)db->uploaded_rows, (long long)db->n_rows);
+    DeviceGuard guard(db->device);
+    if (db->flags & FCS_DB_NORMALISE_ROWS) FCS_CUDA(normalise_rows_launch(db->rows, db->n_rows, 1e-8f, db->stream));
+    if (db->flags & FCS_DB_KEEP_BF16) FCS_CUDA(rows_to_bf16_launch(db->rows, db->rows_bf16, db->n_rows, db->stream));
+    int bad = 0;
+    FCS_CUDA(cudaMemcpyAsync(&bad, db->d_bad, sizeof(int), cudaMemcpyDeviceToHost, db->stream));
+    FCS_CUDA(cudaStreamSynchronize(db->stream));
+    if (bad) return fail(FCS_ERR_INVALID, "fcs_db_finalize: a domain length was outside [0, 65535]");
+    for (int i = 0; i < 2; ++i) {  // upload staging is no longer needed
+        if (db->h_stage[i]) cudaFreeHost(db->h_stage[i]);
+        db->h_stage[i] = nullptr;
+    }
+    if (db->flags & FCS_DB_KEEP_BF16) {
+        int rc = tc_create(&db->tc, db->device, db->sm_count, db->rows, db->rows_bf16, db->n_rows, uint32_t(db->id_offset));
+        if (rc != FCS_OK) return fail(rc, "fcs_db_finalize: tensor-core path setup failed: %s", tc_last_error());
+    }
+    db->finalized = true;
+    return FCS_OK;
+}
+
+// ------------------------------------------------------------------------------------ search
+static int check_search(const fcs_db* db, const void* q, int nq, int k, int qnorm, int mode, const char* fn) {
+    if (!db) return fail(FCS_ERR_INVALID, "%s: db is NULL", fn);
+    if (!db->finalized) return fail(FCS_ERR_STATE, "%s: database not finalized", fn);
+    if (!q) return fail(FCS_ERR_INVALID, "%s: q is NULL", fn);
+    if (nq < 1) return fail(FCS_ERR_INVALID, "%s: nq must be >= 1 (got %d)", fn, nq);
+    if (k < 1 || k > FCS_MAX_K) return fail(FCS_ERR_UNSUPPORTED, "%s: k must be in [1, %d] (got %d)", fn, FCS_MAX_K, k);
+    if (qnorm < FCS_QNORM_NONE || qnorm > FCS_QNORM_L2) return fail(FCS_ERR_INVALID, "%s: bad qnorm %d", fn, qnorm);
+    if (mode < FCS_MODE_AUTO || mode > FCS_MODE_TC) return fail(FCS_ERR_INVALID, "%s: bad mode %d", fn, mode);
+    if (mode == FCS_MODE_TC && !db->tc) return fail(FCS_ERR_STATE, "%s: FCS_MODE_TC needs a database created with FCS_DB_KEEP_BF16", fn);
+    return FCS_OK;
+}
+
+// GEMV path for nq queries (device pointers), all passes enqueued on `stream`.
+static int gemv_search(fcs_db* db, const float* q_dev, int nq, const int32_t* qlen, float mincov, int k, int qnorm,
+                       float* out_scores, int64_t* out_ids, uint64_t* out_keys, cudaStream_t stream, int* launches) {
+    const bool use_mask = qlen != nullptr && db->lens != nullptr;
+    for (int q0 = 0; q0 < nq; q0 += GEMV_MAX_NQ) {
+        const int nqg = (nq - q0 < GEMV_MAX_NQ) ? (nq - q0) : GEMV_MAX_NQ;
+        for (int off = 0; off < k; off += GEMV_MAX_K) {
+            GemvParams p = {};
+            p.rows = db->rows;
+            p.lens = db->lens;
+            p.n_rows = db->n_rows;
+            p.id_base = uint32_t(db->id_offset);
+            p.q = q_dev + size_t(q0) * DIM;
+            p.nq = nqg;
+            p.qnorm = qnorm;
+            p.use_mask = use_mask ? 1 : 0;
+            p.mincov = mincov;
+            for (int i = 0; i < nqg; ++i) p.qlen[i] = use_mask ? float(qlen[q0 + i]) : 0.f;
+            p.k = (k - off < GEMV_MAX_K) ? (k - off) : GEMV_MAX_K;
+            p.out_stride = k;
+            p.out_off = off;
+            p.bounded = off > 0 ? 1 : 0;
+            p.scratch = db->gemv_scratch;
+            p.ticket = db->ticket;
+            p.out_keys = out_keys + size_t(q0) * k;
+            p.out_scores = out_scores ? out_scores + size_t(q0) * k : nullptr;
+            p.out_ids = out_ids ? out_ids + size_t(q0) * k : nullptr;
+            FCS_CUDA(gemv_launch(p, db->sm_count, stream));
+            ++*launches;
+        }
+    }
+    return FCS_OK;
+}
+
+static int search_core(fcs_db* db, const float* q_dev, int nq, const int32_t* qlen, float mincov, int k, int qnorm, int mode,
+                       int kprime, float* out_scores, int64_t* out_ids, uint64_t* out_keys, cudaStream_t stream) {
+    int use_mode = mode;
+    const bool mask_on = qlen != nullptr && db->lens != nullptr;
+    if (use_mode == FCS_MODE_AUTO) use_mode = (db->tc && !mask_on && nq >= tc_min_batch() && k <= tc_max_k()) ? FCS_MODE_TC : FCS_MODE_GEMV;
+    if (use_mode == FCS_MODE_TC && mask_on)
+        return fail(FCS_ERR_UNSUPPORTED, "FCS_MODE_TC does not apply the coverage mask (the faiss flavour has none, dbsearch.py:307-310)");
+    if (use_mode == FCS_MODE_TC && k > tc_max_k())
+        return fail(FCS_ERR_UNSUPPORTED, "FCS_MODE_TC supports k <= %d (got %d)", tc_max_k(), k);
+    int launches = 0;
+    int fallbacks = 0;
+    FCS_CUDA(cudaEventRecord(db->ev0, stream));
+    int rc;
+    if (use_mode == FCS_MODE_GEMV) {
+        rc = gemv_search(db, q_dev, nq, qlen, mincov, k, qnorm, out_scores, out_ids, out_keys, stream, &launches);
+    } else {
+        rc = tc_search(db->tc, q_dev, nq, k, kprime, qnorm, out_scores, out_ids, out_keys, stream, &launches, &fallbacks);
+        if (rc != FCS_OK) return fail(rc, "tensor-core search failed: %s", tc_last_error());
+    }
+    if (rc != FCS_OK) return rc;
+    FCS_CUDA(cudaEventRecord(db->ev1, stream));
+    db->ev_valid = true;
+    db->timing.last_mode = use_mode;
+    db->timing.last_launches = launches;
+    db->timing.last_tc_fallbacks = fallbacks;
+    return FCS_OK;
+}
+
+extern "C" int fcs_search_device(fcs_db* db, const float* q_dev, int nq, const int32_t* qlen, float mincov, int k, int qnorm,
+                                 int mode, int kprime, float* out_scores_dev, int64_t* out_ids_dev, uint64_t* out_keys_dev,
+                                 void* stream) {
+    int rc = check_search(db, q_dev, nq, k, qnorm, mode, "fcs_search_device");
+    if (rc != FCS_OK) return rc;
+    DeviceGuard guard(db->device);
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : db->stream;
+    uint64_t* keys = out_keys_dev;
+    if (!keys) {
+        rc = ensure_out_bufs(db, size_t(nq) * k, false);
+        if (rc != FCS_OK) return rc;
+        keys = db->d_keys;
+    }
+    return search_core(db, q_dev, nq, qlen, mincov, k, qnorm, mode, kprime, out_scores_dev, out_ids_dev, keys, st);
+}
+
+extern "C" int fcs_search(fcs_db* db, const float* q, int nq, const int32_t* qlen, float mincov, int k, int qnorm, int mode,
+                          int kprime, float* out_scores, int64_t* out_ids) {
+    int rc = check_search(db, q, nq, k, qnorm, mode, "fcs_search");
+    if (rc != FCS_OK) return rc;
+    if (!out_scores || !out_ids) return fail(FCS_ERR_INVALID, "fcs_search: output buffer is NULL");
+    DeviceGuard guard(db->device);
+    const size_t entries = size_t(nq) * k;
+    if ((rc = ensure_query_bufs(db, size_t(nq), true)) != FCS_OK) return rc;
+    if ((rc = ensure_out_bufs(db, entries, true)) != FCS_OK) return rc;
+    memcpy(db->h_q, q, size_t(nq) * DIM * sizeof(float));
+    FCS_CUDA(cudaMemcpyAsync(db->d_q, db->h_q, size_t(nq) * DIM * sizeof(float), cudaMemcpyHostToDevice, db->stream));
+    rc = search_core(db, db->d_q, nq, qlen, mincov, k, qnorm, mode, kprime, db->d_scores, db->d_ids, db->d_keys, db->stream);
+    if (rc != FCS_OK) return rc;
+    FCS_CUDA(cudaMemcpyAsync(db->h_scores, db->d_scores, entries * sizeof(float), cudaMemcpyDeviceToHost, db->stream));
+    FCS_CUDA(cudaMemcpyAsync(db->h_ids, db->d_ids, entries * sizeof(int64_t), cudaMemcpyDeviceToHost, db->stream));
+    FCS_CUDA(cudaStreamSynchronize(db->stream));
+    memcpy(out_scores, db->h_scores, entries * sizeof(float));
+    memcpy(out_ids, db->h_ids, entries * sizeof(int64_t));
+    return FCS_OK;
+}
+
+extern "C" int fcs_merge_topk(int device, const uint64_t* keys_dev, int n_lists, int nq, int k, float* out_scores_dev,
+                              int64_t* out_ids_dev, void* stream) {
+    if (!keys_dev) return fail(FCS_ERR_INVALID, "fcs_merge_topk: keys_dev is NULL");
+    if (n_lists < 1 || nq < 1 || k < 1) return fail(FCS_ERR_INVALID, "fcs_merge_topk: n_lists, nq and k must be >= 1");
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(FCS_ERR_CUDA, "fcs_merge_topk: cudaSetDevice(%d) failed", device);
+    FCS_CUDA(merge_topk_launch(keys_dev, n_lists, nq, k, out_scores_dev, out_ids_dev, nullptr, static_cast<cudaStream_t>(stream)));
+    return FCS_OK;
+}
+
+extern "C" int fcs_get_timing(const fcs_db* db_c, fcs_timing* out) {
+    if (!db_c || !out) return fail(FCS_ERR_INVALID, "fcs_get_timing: NULL argument");
+    fcs_db* db = const_cast<fcs_db*>(db_c);
+    DeviceGuard guard(db->device);
+    if (db->ev_valid) {
+        FCS_CUDA(cudaEventSynchronize(db->ev1));
+        float ms = 0.f;
+        FCS_CUDA(cudaEventElapsedTime(&ms, db->ev0, db->ev1));
+        db->timing.last_search_ms = ms;
+        db->timing.last_kernel_ms = ms;
+    }
+    *out = db->timing;
+    return FCS_OK;
+}

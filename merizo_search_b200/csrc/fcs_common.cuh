@@ -1,0 +1,180 @@
+// fcs_common.cuh -- shared device helpers: packed sort keys, warp-resident top-k lists,
+// mbarrier / bulk-copy (TMA) PTX wrappers.  sm_100a only.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace fcs {
+
+constexpr int DIM = 128;
+constexpr int ROW_BYTES = DIM * 4;
+constexpr unsigned FULL = 0xffffffffu;
+
+// --------------------------------------------------------------------------------------
+// Packed sort key: high 32 bits = order-preserving image of the fp32 score, low 32 bits =
+// 0xFFFFFFFF - row id.  Bigger key == better hit (higher score; ties -> lower id), so one
+// unsigned 64-bit compare orders hits deterministically.  Key 0 == empty slot: it is below
+// every real key (the low word of a real key is >= 1 because ids are < 0xFFFFFFFF) and
+// decodes to (-inf, -1), faiss's padding convention.
+// --------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint32_t order_f32(float f) {
+#ifdef __CUDA_ARCH__
+    uint32_t b = __float_as_uint(f);
+#else
+    uint32_t b;
+    memcpy(&b, &f, 4);
+#endif
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__host__ __device__ __forceinline__ float unorder_f32(uint32_t u) {
+    uint32_t b = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(b);
+#else
+    float f;
+    memcpy(&f, &b, 4);
+    return f;
+#endif
+}
+__host__ __device__ __forceinline__ uint64_t make_key(float score, uint32_t id) {
+    return (uint64_t(order_f32(score)) << 32) | uint64_t(0xFFFFFFFFu - id);
+}
+__host__ __device__ __forceinline__ float key_score(uint64_t key) {
+    return key == 0 ? -INFINITY : unorder_f32(uint32_t(key >> 32));
+}
+__host__ __device__ __forceinline__ int64_t key_id(uint64_t key) {
+    return key == 0 ? int64_t(-1) : int64_t(0xFFFFFFFFu - uint32_t(key));
+}
+
+#ifdef __CUDACC__
+__device__ __forceinline__ uint64_t shfl_u64(uint64_t v, int src) {
+    uint32_t lo = __shfl_sync(FULL, uint32_t(v), src);
+    uint32_t hi = __shfl_sync(FULL, uint32_t(v >> 32), src);
+    return (uint64_t(hi) << 32) | lo;
+}
+__device__ __forceinline__ uint64_t shfl_up_u64(uint64_t v, int d) {
+    uint32_t lo = __shfl_up_sync(FULL, uint32_t(v), d);
+    uint32_t hi = __shfl_up_sync(FULL, uint32_t(v >> 32), d);
+    return (uint64_t(hi) << 32) | lo;
+}
+
+// --------------------------------------------------------------------------------------
+// Warp-resident sorted top-k list.  Rank r (0 = best) lives in lane (r % 32), register
+// slot (r / 32); capacity 32*KPL >= k.  `thr` is the key at rank k-1 (0 while the list
+// holds fewer than k hits): a candidate enters only if its key beats thr, which after a
+// short warm-up is rare (about k*ln(n/k) times over n rows), so the streaming loop pays
+// one compare + one ballot per 32 rows.
+// --------------------------------------------------------------------------------------
+template <int KPL>
+struct WarpTopK {
+    uint64_t key[KPL];
+    uint64_t thr;
+
+    __device__ __forceinline__ void init() {
+#pragma unroll
+        for (int j = 0; j < KPL; ++j) key[j] = 0;
+        thr = 0;
+    }
+
+    // Each lane offers one candidate (cand == 0 -> none).  Warp-uniform control flow.
+    __device__ __forceinline__ void offer(uint64_t cand, int lane, int k) {
+        unsigned m = __ballot_sync(FULL, cand > thr);
+        while (m) {
+            const int src = __ffs(m) - 1;
+            const uint64_t nk = shfl_u64(cand, src);
+            insert(nk, lane, k);
+            m &= m - 1;
+            m &= __ballot_sync(FULL, cand > thr);
+        }
+    }
+
+    // All 32 lanes call with the same nk.  Inserts nk at its sorted position; the last rank falls
+    // off.  The runtime (k-1)>>5 register index is resolved by a small unrolled select.
+    __device__ __forceinline__ void insert(uint64_t nk, int lane, int k) {
+        int p = 0;
+#pragma unroll
+        for (int j = 0; j < KPL; ++j) p += __popc(__ballot_sync(FULL, key[j] > nk));
+#pragma unroll
+        for (int j = KPL - 1; j >= 0; --j) {
+            uint64_t up = shfl_up_u64(key[j], 1);
+            if (j > 0) {
+                uint64_t wrap = shfl_u64(key[j - 1], 31);
+                if (lane == 0) up = wrap;
+            }
+            const int r = j * 32 + lane;
+            key[j] = (r > p) ? up : ((r == p) ? nk : key[j]);
+        }
+        const int slot = (k - 1) >> 5;
+        uint64_t sel = key[0];
+#pragma unroll
+        for (int j = 1; j < KPL; ++j) sel = (slot == j) ? key[j] : sel;
+        thr = shfl_u64(sel, (k - 1) & 31);
+    }
+
+    // rank r -> key (r in [0, 32*KPL)); caller picks lane/slot: helper to store the first k ranks
+    __device__ __forceinline__ void store(uint64_t* dst, int lane, int k) const {
+#pragma unroll
+        for (int j = 0; j < KPL; ++j) {
+            const int r = j * 32 + lane;
+            if (r < k) dst[r] = key[j];
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------- mbarrier / TMA
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+// 1-D bulk asynchronous copy global -> shared (the TMA engine's non-tensor form; SASS: UBLKCP).
+// dst/src 16-byte aligned, bytes a multiple of 16.  Completion is signalled on `bar` (complete_tx).
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar,
+                                         uint64_t cache_policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(cache_policy)
+        : "memory");
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t policy_evict_normal() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+#endif  // __CUDACC__
+
+}  // namespace fcs

@@ -1,0 +1,187 @@
+"""ctypes binding of libfcsearch.so (include/fcsearch.h) -- thin, no compute, no fallback.
+
+Every product entry point goes through here; if the CUDA library is missing or the call
+fails, ``FcsError`` is raised -- there is no CPU path behind this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import numpy as np
+
+from . import build as _build
+
+DIM = 128
+MAX_K = 2048
+
+# error codes / flags / enums (mirrors include/fcsearch.h)
+OK, ERR_INVALID, ERR_CUDA, ERR_STATE, ERR_UNSUPPORTED, ERR_NOMEM = 0, -1, -2, -3, -4, -5
+DB_NORMALISE_ROWS, DB_KEEP_BF16, DB_HAS_LENGTHS = 1, 2, 4
+QNORM_NONE, QNORM_COSINE, QNORM_L2 = 0, 1, 2
+MODE_AUTO, MODE_GEMV, MODE_TC = 0, 1, 2
+
+EXPORTS = [
+    "fcs_version", "fcs_last_error", "fcs_device_count", "fcs_db_create", "fcs_db_upload",
+    "fcs_db_upload_device", "fcs_db_finalize", "fcs_db_get_info", "fcs_db_destroy", "fcs_search",
+    "fcs_search_device", "fcs_merge_topk", "fcs_get_timing",
+]
+
+
+class FcsError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libfcsearch error {code}: {msg}")
+        self.code = code
+
+
+class Timing(C.Structure):
+    _fields_ = [("last_search_ms", C.c_float), ("last_kernel_ms", C.c_float), ("last_mode", C.c_int32),
+                ("last_launches", C.c_int32), ("last_tc_fallbacks", C.c_int32), ("reserved", C.c_int32)]
+
+
+class Info(C.Structure):
+    _fields_ = [("n_rows", C.c_int64), ("id_offset", C.c_int64), ("device", C.c_int32), ("flags", C.c_uint32),
+                ("finalized", C.c_int32), ("sm_count", C.c_int32), ("bytes_fp32", C.c_uint64), ("bytes_bf16", C.c_uint64)]
+
+
+_lib: Optional[C.CDLL] = None
+
+
+def lib_path() -> str:
+    return _build.LIB_PATH
+
+
+def load() -> C.CDLL:
+    """dlopen libfcsearch.so (building it first if the sources are newer) and type its exports."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB_PATH
+    if not os.path.exists(path) or (not _build.is_fresh() and os.environ.get("FCS_NO_REBUILD") != "1"):
+        try:
+            _build.build()
+        except Exception as exc:  # no silent fallback: the product needs the CUDA library
+            if not os.path.exists(path):
+                raise FcsError(ERR_STATE, f"libfcsearch.so is missing and could not be built: {exc}") from exc
+    lib = C.CDLL(path)
+    vp, i64, i32, u32, f32 = C.c_void_p, C.c_int64, C.c_int, C.c_uint32, C.c_float
+    lib.fcs_version.restype = C.c_int
+    lib.fcs_version.argtypes = []
+    lib.fcs_last_error.restype = C.c_char_p
+    lib.fcs_last_error.argtypes = []
+    lib.fcs_device_count.argtypes = [C.POINTER(C.c_int)]
+    lib.fcs_db_create.argtypes = [i32, i64, i32, i64, u32, C.POINTER(vp)]
+    lib.fcs_db_upload.argtypes = [vp, i64, i64, vp, vp]
+    lib.fcs_db_upload_device.argtypes = [vp, i64, i64, vp, vp]
+    lib.fcs_db_finalize.argtypes = [vp]
+    lib.fcs_db_get_info.argtypes = [vp, C.POINTER(Info)]
+    lib.fcs_db_destroy.argtypes = [vp]
+    lib.fcs_search.argtypes = [vp, vp, i32, vp, f32, i32, i32, i32, i32, vp, vp]
+    lib.fcs_search_device.argtypes = [vp, vp, i32, vp, f32, i32, i32, i32, i32, vp, vp, vp, vp]
+    lib.fcs_merge_topk.argtypes = [i32, vp, i32, i32, i32, vp, vp, vp]
+    lib.fcs_get_timing.argtypes = [vp, C.POINTER(Timing)]
+    for name in EXPORTS:
+        if name not in ("fcs_last_error",):
+            getattr(lib, name).restype = C.c_int
+    lib.fcs_last_error.restype = C.c_char_p
+    _lib = lib
+    return lib
+
+
+def _check(rc: int) -> None:
+    if rc != OK:
+        raise FcsError(rc, load().fcs_last_error().decode("utf-8", "replace"))
+
+
+def device_count() -> int:
+    n = C.c_int(0)
+    _check(load().fcs_device_count(C.byref(n)))
+    return n.value
+
+
+def _np_ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Database:
+    """One device-resident row shard (fcs_db).  Not re-entrant; do not share across forks."""
+
+    def __init__(self, n_rows: int, device: int = 0, id_offset: int = 0, normalise_rows: bool = False,
+                 keep_bf16: bool = False, has_lengths: bool = False):
+        self._lib = load()
+        self._h = C.c_void_p()
+        flags = (DB_NORMALISE_ROWS if normalise_rows else 0) | (DB_KEEP_BF16 if keep_bf16 else 0) | \
+                (DB_HAS_LENGTHS if has_lengths else 0)
+        _check(self._lib.fcs_db_create(int(device), int(n_rows), DIM, int(id_offset), flags, C.byref(self._h)))
+        self.n_rows, self.device, self.id_offset, self.flags = int(n_rows), int(device), int(id_offset), flags
+        self.has_lengths = bool(has_lengths)
+
+    # -- loading ---------------------------------------------------------------------------
+    def upload(self, row0: int, rows: np.ndarray, lengths: Optional[np.ndarray] = None) -> None:
+        rows = np.ascontiguousarray(rows, dtype=np.float32)
+        if rows.ndim != 2 or rows.shape[1] != DIM:
+            raise FcsError(ERR_INVALID, f"rows must be [n,{DIM}] float32, got {rows.shape}")
+        lens = None if lengths is None else np.ascontiguousarray(lengths, dtype=np.int32)
+        if lens is not None and lens.shape[0] != rows.shape[0]:
+            raise FcsError(ERR_INVALID, "lengths and rows disagree on the row count")
+        _check(self._lib.fcs_db_upload(self._h, int(row0), rows.shape[0], _np_ptr(rows), _np_ptr(lens)))
+
+    def upload_device(self, row0: int, n: int, rows_ptr: int, lengths_ptr: Optional[int] = None) -> None:
+        _check(self._lib.fcs_db_upload_device(self._h, int(row0), int(n), C.c_void_p(rows_ptr),
+                                              C.c_void_p(lengths_ptr) if lengths_ptr else None))
+
+    def finalize(self) -> None:
+        _check(self._lib.fcs_db_finalize(self._h))
+
+    # -- search ----------------------------------------------------------------------------
+    def search(self, q: np.ndarray, k: int, qlen: Optional[np.ndarray] = None, mincov: float = 0.0,
+               qnorm: int = QNORM_NONE, mode: int = MODE_AUTO, kprime: int = 0):
+        """Host buffers in, host buffers out: (scores f32 [nq,k], ids i64 [nq,k])."""
+        q = np.ascontiguousarray(q, dtype=np.float32).reshape(-1, DIM)
+        nq = q.shape[0]
+        ql = None if qlen is None else np.ascontiguousarray(qlen, dtype=np.int32).reshape(-1)
+        if ql is not None and ql.shape[0] != nq:
+            raise FcsError(ERR_INVALID, "qlen must have one entry per query")
+        scores = np.empty((nq, int(k)), dtype=np.float32)
+        ids = np.empty((nq, int(k)), dtype=np.int64)
+        _check(self._lib.fcs_search(self._h, _np_ptr(q), nq, _np_ptr(ql), float(mincov), int(k), int(qnorm), int(mode),
+                                    int(kprime), _np_ptr(scores), _np_ptr(ids)))
+        return scores, ids
+
+    def search_device(self, q_ptr: int, nq: int, k: int, out_scores_ptr: int, out_ids_ptr: int,
+                      out_keys_ptr: int = 0, qlen: Optional[np.ndarray] = None, mincov: float = 0.0,
+                      qnorm: int = QNORM_NONE, mode: int = MODE_AUTO, kprime: int = 0, stream: int = 0) -> None:
+        """Device pointers, asynchronous on `stream` (0 = the handle's own stream)."""
+        ql = None if qlen is None else np.ascontiguousarray(qlen, dtype=np.int32).reshape(-1)
+        _check(self._lib.fcs_search_device(
+            self._h, C.c_void_p(q_ptr), int(nq), _np_ptr(ql), float(mincov), int(k), int(qnorm), int(mode), int(kprime),
+            C.c_void_p(out_scores_ptr) if out_scores_ptr else None, C.c_void_p(out_ids_ptr) if out_ids_ptr else None,
+            C.c_void_p(out_keys_ptr) if out_keys_ptr else None, C.c_void_p(stream) if stream else None))
+
+    def timing(self) -> Timing:
+        t = Timing()
+        _check(self._lib.fcs_get_timing(self._h, C.byref(t)))
+        return t
+
+    def info(self) -> Info:
+        i = Info()
+        _check(self._lib.fcs_db_get_info(self._h, C.byref(i)))
+        return i
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.fcs_db_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def merge_topk(device: int, keys_ptr: int, n_lists: int, nq: int, k: int, out_scores_ptr: int, out_ids_ptr: int,
+               stream: int = 0) -> None:
+    _check(load().fcs_merge_topk(int(device), C.c_void_p(keys_ptr), int(n_lists), int(nq), int(k),
+                                 C.c_void_p(out_scores_ptr), C.c_void_p(out_ids_ptr), C.c_void_p(stream) if stream else None))
