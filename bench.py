@@ -1,0 +1,388 @@
+#!/usr/bin/env python
+"""bench.py -- queries/s of the Foldclass database search on N B200s (one rank per GPU).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2|cfg3|cfg4] [--impl reference]
+
+Workloads (BASELINE.json `configs`, synthetic unit-norm 128-d rows, random queries):
+  cfg3 (default)  10 M rows, 4096-query batch, k=100      -- tcgen05 path; largest single-GPU config
+  cfg2            500 k rows (CATH scale), 1 query, k=10  -- fp32 scan (GEMV) path, coverage mask on
+  cfg4            45.625 M rows PER GPU (365 M / 8), 1 query, k=10 -- fp32 scan, TED-scale slice
+With N>1 the database of cfg2/cfg3 is row-sharded over the ranks (strong scaling); cfg4 keeps
+45.625 M rows per rank (weak scaling; at N=8 it is the full 365 M-row TED database).  The per-rank
+key lists are exchanged with ONE NCCL all-gather and merged on the GPU.
+
+One JSON line on stdout (rank 0).  `value` = queries/s with queries and database resident in HBM,
+timed with CUDA events over K steps (max over ranks).  `e2e` = the same through the host-buffer API
+(pinned host queries in, host results out, copies inside the timed region).  `roofline` is for the
+dominant kernel (tcgen05 GEMM+filter for cfg3, fp32 scan for cfg2/cfg4).  `cpu_baseline` = the CPU
+oracle (a port of the reference's torch / faiss-flat arithmetic) on this box's host cores on a bounded
+sample.  `--impl reference` times only that CPU arm (the reference is pure Python + torch/faiss and
+cannot travel to the GPU box).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    "cfg2": dict(rows=500_000, nq=1, k=10, mode="gemv", mask=True, scaling="strong",
+                 desc="BASELINE configs[1]: synthetic CATH-4.3-scale DB 500k x 128 fp32, single query, k=10, fp32 scan path"),
+    "cfg3": dict(rows=10_000_000, nq=4096, k=100, mode="tc", mask=False, scaling="strong",
+                 desc="BASELINE configs[2]: synthetic 10M x 128 DB, 4096-query batch, k=100, tcgen05 path"),
+    "cfg4": dict(rows=45_625_000, nq=1, k=10, mode="gemv", mask=False, scaling="weak",
+                 desc="BASELINE configs[3] slice: 365M/8 = 45.625M x 128 fp32 rows per GPU, single query, k=10, fp32 scan path"),
+}
+DEFAULT_WORKLOAD = "cfg3"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            d = json.load(fh)
+        return dict(hbm=float(d["hbm_gbs"]), tensor=float(d["bf16_tflops_sustained"]), tensor_burst=float(d["bf16_tflops"]),
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tensor=1400.0, tensor_burst=1590.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, gpu_index: int):
+        self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(gpu_index)], stdout=self.tmp, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.tmp.flush()
+        self.tmp.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.tmp.read().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        try:
+            os.unlink(self.tmp.name)
+        except OSError:
+            pass
+        if sm:
+            top = sorted(sm)[len(sm) // 2:]  # samples under load dominate the upper half
+            out["sm_mhz"] = float(np.median(top))
+            out["sm_max_mhz"] = float(max(mx))
+        out["reasons"] = sorted(reasons)
+        out["samples"] = len(sm)
+        return out
+
+
+# --------------------------------------------------------------------------------------------- CPU arm
+def cpu_oracle_throughput(wl, n_rows_total, budget_s=12.0):
+    """Queries/s of the CPU oracle (port of the reference arithmetic) on a bounded sample, all host threads.
+
+    torch flavour (cfg2): the reference's own three lines (cosine_similarity * mask -> topk) per query on the
+    full 500k DB.  faiss flavour (cfg3/cfg4): blockwise mm + topk + merge restatement on a row sample,
+    extrapolated linearly in the row count (stated in `sample`).
+    """
+    import torch
+
+    from merizo_search_b200 import synth
+    from oracle import foldclass_oracle as orc
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    k, nq = wl["k"], wl["nq"]
+    if wl["mask"]:
+        n = min(n_rows_total, 500_000)
+        db = torch.from_numpy(synth.host_db(n, base_seed=1, normalise=False))
+        lens = torch.from_numpy(synth.host_lengths(n).astype(np.float32))
+        q = torch.from_numpy(synth.host_queries(8, 5))
+        orc.search_torch_flavour(db, lens, q[0], 150, 0.7, k)  # warm
+        t0, done = time.perf_counter(), 0
+        while time.perf_counter() - t0 < budget_s and done < 64:
+            orc.search_torch_flavour(db, lens, q[done % 8], 150, 0.7, k)
+            done += 1
+        dt = time.perf_counter() - t0
+        qps = done / dt * (n / n_rows_total)
+        sample = f"{done} queries x {n} rows, reference torch arithmetic (cosine_similarity*mask->topk), {dt:.1f} s"
+        return qps, cores, sample
+    n = min(n_rows_total, 262_144 * (1 if nq >= 1024 else 8))
+    nq_s = min(nq, 4096)
+    db = synth.host_db(n, base_seed=1)
+    q = synth.host_queries(nq_s, 5, normalise=True)
+    orc.knn_exact_blockwise(q[: min(nq_s, 64)], orc.db_iterator(db[:65536], 65536), k)  # warm
+    t0 = time.perf_counter()
+    reps = 0
+    while True:
+        orc.knn_exact_blockwise(q, orc.db_iterator(db, 262_144), k)
+        reps += 1
+        if time.perf_counter() - t0 > budget_s * 0.5 or reps >= 20:
+            break
+    dt = (time.perf_counter() - t0) / reps
+    qps = nq_s / dt * (n / n_rows_total)
+    sample = (f"{nq_s} queries x {n} rows (of {n_rows_total}), blockwise mm+topk+merge restatement of faiss IndexFlatIP "
+              f"(262144-row blocks), {dt:.2f} s/pass x {reps}, extrapolated linearly in rows")
+    return qps, cores, sample
+
+
+# --------------------------------------------------------------------------------------------- GPU arm
+def run_gpu(args, wl, wl_name):
+    import torch
+    import torch.distributed as dist
+
+    from merizo_search_b200 import native, synth
+    from merizo_search_b200.engine import shard_ranges
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N > 1")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    peaks = load_peaks()
+    nq, k = wl["nq"], wl["k"]
+    rows_total = wl["rows"] * (world if wl["scaling"] == "weak" else 1)
+    if args.rows:
+        rows_total = args.rows
+    r0, r1 = shard_ranges(rows_total, world)[rank]
+    n_local = r1 - r0
+    mode = native.MODE_TC if wl["mode"] == "tc" else native.MODE_GEMV
+
+    # ---- database: generated on the device block by block, uploaded into the handle, finalized
+    t_load = time.perf_counter()
+    h = native.Database(n_local, device=local_rank, id_offset=r0, keep_bf16=(wl["mode"] == "tc"), has_lengths=wl["mask"])
+    blk = 1 << 20
+    lens_all = None
+    if wl["mask"]:
+        lens_all = torch.from_numpy(synth.host_lengths(rows_total)[r0:r1].astype(np.int32)).to(dev)
+    for b0 in range(0, n_local, blk):
+        nb = min(blk, n_local - b0)
+        x = synth.device_block((r0 + b0) // blk, nb, dev, base_seed=1000)
+        h.upload_device(b0, nb, x.data_ptr(), lens_all[b0:b0 + nb].contiguous().data_ptr() if wl["mask"] else None)
+        del x
+    h.finalize()
+    torch.cuda.synchronize()
+    t_load = time.perf_counter() - t_load
+
+    g = torch.Generator(device=dev)
+    g.manual_seed(4242)  # same queries on every rank (replicated)
+    q_dev = torch.nn.functional.normalize(torch.randn((nq, 128), device=dev, generator=g))
+    q_host = q_dev.cpu().pin_memory()
+    qlen = np.full(nq, 150, np.int32) if wl["mask"] else None
+    mincov = 0.7 if wl["mask"] else 0.0
+
+    stream = torch.cuda.Stream(dev)
+    keys = torch.empty((nq, k), dtype=torch.int64, device=dev)
+    sc = torch.empty((nq, k), dtype=torch.float32, device=dev)
+    ids = torch.empty((nq, k), dtype=torch.int64, device=dev)
+    gathered = torch.empty((world, nq, k), dtype=torch.int64, device=dev) if world > 1 else None
+    launches = 0
+
+    def step_device():
+        nonlocal launches
+        with torch.cuda.stream(stream):
+            h.search_device(q_dev.data_ptr(), nq, k, sc.data_ptr(), ids.data_ptr(), out_keys_ptr=keys.data_ptr(),
+                            qlen=qlen, mincov=mincov, mode=mode, stream=stream.cuda_stream)
+            launches += launches_per_search
+            if world > 1:
+                dist.all_gather_into_tensor(gathered.view(world * nq, k), keys)
+                native.merge_topk(local_rank, gathered.data_ptr(), world, nq, k, sc.data_ptr(), ids.data_ptr(),
+                                  stream=stream.cuda_stream)
+                launches += 1
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    launches_per_search = 0
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    launches_per_search = int(h.timing().last_launches)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    launches = 0
+    kernel_ms = []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        e0.record()
+    for _ in range(args.steps):
+        step_device()
+        if wl["mode"] == "tc":
+            kernel_ms.append(h.timing().last_kernel_ms)  # the TC path already synchronised the stream
+    with torch.cuda.stream(stream):
+        e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop() if sampler else None
+    if wl["mode"] != "tc":
+        kernel_ms = [ms_total / args.steps]  # one kernel per step, launched back to back
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_per_step = ms_total / args.steps
+    value = nq / (ms_per_step * 1e-3)
+    timing = h.timing()
+
+    # ---- e2e: host buffers through the public host API (H2D + D2H inside the timed region)
+    def step_e2e():
+        s_h, i_h = h.search(q_host.numpy(), k, qlen=qlen, mincov=mincov, mode=mode)
+        if world > 1:
+            from merizo_search_b200.engine import encode_keys
+            kh = torch.from_numpy(encode_keys(s_h, i_h).view(np.int64)).pin_memory()
+            with torch.cuda.stream(stream):
+                keys.copy_(kh, non_blocking=True)
+                dist.all_gather_into_tensor(gathered.view(world * nq, k), keys)
+                native.merge_topk(local_rank, gathered.data_ptr(), world, nq, k, sc.data_ptr(), ids.data_ptr(),
+                                  stream=stream.cuda_stream)
+                s_h = sc.cpu()
+                i_h = ids.cpu()
+        return s_h, i_h
+
+    for _ in range(max(1, args.warmup // 2)):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / args.steps
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+
+    out = None
+    if rank == 0:
+        kms = float(np.mean(kernel_ms))
+        if wl["mode"] == "tc":
+            flops = 2.0 * nq * n_local * 128
+            achieved = flops / (kms * 1e-3) / 1e12
+            roof = dict(bound="tensor", achieved=achieved, peak=peaks["tensor"], unit="TFLOP/s", frac=achieved / peaks["tensor"],
+                        traffic=None, kernel="tc_gemm_filter_kernel (all rounds of one search)",
+                        algorithmic="2*nq*rows*128 flop per search", peak_source=peaks["source"] + ", sustained bf16")
+        else:
+            bpr = 512 + (2 if wl["mask"] else 0)
+            byts = float(n_local) * bpr
+            achieved = byts / (kms * 1e-3) / 1e9
+            roof = dict(bound="hbm", achieved=achieved, peak=peaks["hbm"], unit="GB/s", frac=achieved / peaks["hbm"], traffic=None,
+                        kernel="gemv_topk_kernel", algorithmic=f"{bpr} B per row per launch", peak_source=peaks["source"])
+        prof = os.path.join(ROOT, "profiles", f"traffic_{wl_name}.json")
+        if os.path.exists(prof):
+            with open(prof) as fh:
+                roof["traffic"] = json.load(fh).get("dram_bytes_per_launch")
+        out = {
+            "metric": "queries/s vs 128-d DB, top-k (exact)", "value": value, "unit": "queries/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": wl["scaling"], "vs_baseline": None,
+            "dtype": "bf16 tensor-core contraction + fp32 exact rescore" if wl["mode"] == "tc" else "f32",
+            "data": "synthetic (i.i.d. N(0,1) rows, L2-normalised, generated on device per 2^20-row block; random unit queries)",
+            "config": {"workload": wl_name, "description": wl["desc"], "rows_total": rows_total, "rows_per_gpu": n_local,
+                       "nq": nq, "k": k, "path": wl["mode"], "coverage_mask": wl["mask"],
+                       "l2": "inputs larger than L2 (database streamed from HBM every step)",
+                       "parallelism": f"row-sharded x{world}, NCCL all-gather of packed keys + GPU merge" if world > 1 else "single GPU",
+                       "db_load_s": round(t_load, 2), "tc_fallback_queries": int(timing.last_tc_fallbacks)},
+            "e2e": {"value": nq / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": int(nq * 512),
+                    "d2h_bytes_per_step": int(nq * k * 12), "ms_per_step": e2e_s * 1e3,
+                    "api": "merizo_search_b200.native.Database.search (fcs_search: pinned host queries in, host scores/ids out)"},
+            "gpu_launches": int(launches),
+            "roofline": roof,
+            "clocks": clocks,
+        }
+    h.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return out, rows_total
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=0)
+    ap.add_argument("--warmup", type=int, default=0)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("FCS_BENCH_WORKLOAD", DEFAULT_WORKLOAD), choices=sorted(WORKLOADS))
+    ap.add_argument("--rows", type=int, default=0, help="override the total row count (debugging)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.steps <= 0:
+        args.steps = 20 if wl["mode"] == "tc" else 200
+    if args.warmup <= 0:
+        args.warmup = 3 if wl["mode"] == "tc" else 10
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        rows_total = args.rows or wl["rows"] * (world if wl["scaling"] == "weak" else 1)
+        vals = []
+        cores = sample = None
+        for _ in range(max(1, min(args.steps, 3))):
+            v, cores, sample = cpu_oracle_throughput(wl, rows_total, budget_s=10.0)
+            vals.append(v)
+        v = float(np.median(vals))
+        print(json.dumps({
+            "impl": "reference", "metric": "queries/s vs 128-d DB, top-k (exact)", "value": v, "unit": "queries/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wl["nq"] / v,
+            "higher_is_better": True, "scaling": wl["scaling"], "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "description": wl["desc"], "rows_total": rows_total, "nq": wl["nq"], "k": wl["k"]},
+            "cpu_baseline": {"value": v, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }))
+        return 0
+
+    out, rows_total = run_gpu(args, wl, args.workload)
+    if rank == 0:
+        if not args.no_cpu_baseline and world == 1:
+            v, cores, sample = cpu_oracle_throughput(wl, rows_total, budget_s=12.0)
+            out["cpu_baseline"] = {"value": v, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample}
+        else:
+            out["cpu_baseline"] = None
+        print(json.dumps(out))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -63,7 +63,7 @@ typedef struct fcs_timing {
     int32_t last_mode;        /* FCS_MODE_GEMV or FCS_MODE_TC actually used */
     int32_t last_launches;    /* kernels launched by that call */
     int32_t last_tc_fallbacks; /* TC path: queries whose exactness certificate failed and were re-run on the GEMV path */
-    int32_t reserved;
+    int32_t last_rounds;      /* TC path: GEMM+filter launches (rounds) of that call; 1 otherwise */
 } fcs_timing;
 
 typedef struct fcs_info {
@@ -120,6 +120,10 @@ int fcs_merge_topk(int device, const uint64_t* keys_dev, int n_lists, int nq, in
                    int64_t* out_ids_dev, void* stream);
 
 int fcs_get_timing(const fcs_db* db, fcs_timing* out);
+
+/* Test hook (not part of the drop-in surface): the approximate bf16 tensor-core score of every
+ * (query,row) pair, out_scores [nq, n_rows] HOST fp32; only for shards of <= 4096 rows. */
+int fcs_debug_tc_approx(fcs_db* db, const float* q, int nq, int qnorm, float* out_scores);
 
 #ifdef __cplusplus
 }

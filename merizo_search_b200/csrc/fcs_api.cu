@@ -47,6 +47,7 @@ struct DeviceGuard {
     }
 };
 constexpr size_t STAGE_BYTES_HOST = size_t(32) << 20;  // pinned staging buffers for fcs_db_upload
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------ handle
@@ -59,8 +60,7 @@ struct fcs_db {
     int sm_count = 0;
     int64_t uploaded_rows = 0;
 
-    float* rows = nullptr;         // [n_rows,128] fp32
-    void* rows_bf16 = nullptr;     // [n_rows,128] bf16 (optional)
+    float* rows = nullptr;         // [n_rows,128] fp32, row-swizzled after finalize
     uint16_t* lens = nullptr;      // [n_rows] (optional)
 
     cudaStream_t stream = nullptr;
@@ -187,7 +187,6 @@ extern "C" int fcs_db_create(int device, int64_t n_rows, int dim, int64_t id_off
         FCS_CUDA(cudaEventCreate(&db->ev1));
         FCS_CUDA(cudaMalloc(&db->rows, size_t(n_rows) * ROW_BYTES));
         if (flags & FCS_DB_HAS_LENGTHS) FCS_CUDA(cudaMalloc(&db->lens, size_t(n_rows) * sizeof(uint16_t)));
-        if (flags & FCS_DB_KEEP_BF16) FCS_CUDA(cudaMalloc(&db->rows_bf16, size_t(n_rows) * DIM * 2));
         FCS_CUDA(cudaMalloc(&db->gemv_scratch, gemv_scratch_bytes(db->sm_count)));
         FCS_CUDA(cudaMalloc(&db->ticket, sizeof(unsigned)));
         FCS_CUDA(cudaMemsetAsync(db->ticket, 0, sizeof(unsigned), db->stream));
@@ -213,7 +212,6 @@ extern "C" int fcs_db_destroy(fcs_db* db) {
     if (db->stream) cudaStreamSynchronize(db->stream);
     if (db->tc) tc_destroy(db->tc);
     cudaFree(db->rows);
-    cudaFree(db->rows_bf16);
     cudaFree(db->lens);
     cudaFree(db->gemv_scratch);
     cudaFree(db->ticket);
@@ -246,7 +244,7 @@ extern "C" int fcs_db_get_info(const fcs_db* db, fcs_info* out) {
     out->finalized = db->finalized ? 1 : 0;
     out->sm_count = db->sm_count;
     out->bytes_fp32 = uint64_t(db->n_rows) * ROW_BYTES;
-    out->bytes_bf16 = db->rows_bf16 ? uint64_t(db->n_rows) * DIM * 2 : 0;
+    out->bytes_bf16 = db->tc ? tc_image_bytes(db->tc) : 0;
     return FCS_OK;
 }
 
@@ -328,8 +326,7 @@ extern "C" int fcs_db_finalize(fcs_db* db) {
     if (db->uploaded_rows < db->n_rows)
         return fail(FCS_ERR_STATE, "fcs_db_finalize: only %lld of %lld rows uploaded", (long long)db->uploaded_rows, (long long)db->n_rows);
     DeviceGuard guard(db->device);
-    if (db->flags & FCS_DB_NORMALISE_ROWS) FCS_CUDA(normalise_rows_launch(db->rows, db->n_rows, 1e-8f, db->stream));
-    if (db->flags & FCS_DB_KEEP_BF16) FCS_CUDA(rows_to_bf16_launch(db->rows, db->rows_bf16, db->n_rows, db->stream));
+    FCS_CUDA(finalize_rows_launch(db->rows, db->n_rows, (db->flags & FCS_DB_NORMALISE_ROWS) ? 1 : 0, 1e-8f, db->stream));
     int bad = 0;
     FCS_CUDA(cudaMemcpyAsync(&bad, db->d_bad, sizeof(int), cudaMemcpyDeviceToHost, db->stream));
     FCS_CUDA(cudaStreamSynchronize(db->stream));
@@ -339,7 +336,7 @@ extern "C" int fcs_db_finalize(fcs_db* db) {
         db->h_stage[i] = nullptr;
     }
     if (db->flags & FCS_DB_KEEP_BF16) {
-        int rc = tc_create(&db->tc, db->device, db->sm_count, db->rows, db->rows_bf16, db->n_rows, uint32_t(db->id_offset));
+        int rc = tc_create(&db->tc, db->device, db->sm_count, db->rows, db->n_rows, uint32_t(db->id_offset), db->stream);
         if (rc != FCS_OK) return fail(rc, "fcs_db_finalize: tensor-core path setup failed: %s", tc_last_error());
     }
     db->finalized = true;
@@ -360,8 +357,8 @@ static int check_search(const fcs_db* db, const void* q, int nq, int k, int qnor
 }
 
 // GEMV path for nq queries (device pointers), all passes enqueued on `stream`.
-static int gemv_search(fcs_db* db, const float* q_dev, int nq, const int32_t* qlen, float mincov, int k, int qnorm,
-                       float* out_scores, int64_t* out_ids, uint64_t* out_keys, cudaStream_t stream, int* launches) {
+static int gemv_search(fcs_db* db, const float* q, int nq, const int32_t* qlen, float mincov, int k,
+                       int qnorm, float* out_scores, int64_t* out_ids, uint64_t* out_keys, cudaStream_t stream, int* launches) {
     const bool use_mask = qlen != nullptr && db->lens != nullptr;
     for (int q0 = 0; q0 < nq; q0 += GEMV_MAX_NQ) {
         const int nqg = (nq - q0 < GEMV_MAX_NQ) ? (nq - q0) : GEMV_MAX_NQ;
@@ -371,7 +368,7 @@ static int gemv_search(fcs_db* db, const float* q_dev, int nq, const int32_t* ql
             p.lens = db->lens;
             p.n_rows = db->n_rows;
             p.id_base = uint32_t(db->id_offset);
-            p.q = q_dev + size_t(q0) * DIM;
+            p.q = q + size_t(q0) * DIM;
             p.nq = nqg;
             p.qnorm = qnorm;
             p.use_mask = use_mask ? 1 : 0;
@@ -393,8 +390,9 @@ static int gemv_search(fcs_db* db, const float* q_dev, int nq, const int32_t* ql
     return FCS_OK;
 }
 
-static int search_core(fcs_db* db, const float* q_dev, int nq, const int32_t* qlen, float mincov, int k, int qnorm, int mode,
-                       int kprime, float* out_scores, int64_t* out_ids, uint64_t* out_keys, cudaStream_t stream) {
+static int search_core(fcs_db* db, const float* q_dev, int nq, const int32_t* qlen, float mincov, int k,
+                       int qnorm, int mode, int kprime, float* out_scores, int64_t* out_ids, uint64_t* out_keys,
+                       cudaStream_t stream) {
     int use_mode = mode;
     const bool mask_on = qlen != nullptr && db->lens != nullptr;
     if (use_mode == FCS_MODE_AUTO) use_mode = (db->tc && !mask_on && nq >= tc_min_batch() && k <= tc_max_k()) ? FCS_MODE_TC : FCS_MODE_GEMV;
@@ -405,12 +403,19 @@ static int search_core(fcs_db* db, const float* q_dev, int nq, const int32_t* ql
     int launches = 0;
     int fallbacks = 0;
     FCS_CUDA(cudaEventRecord(db->ev0, stream));
-    int rc;
+    int rc = FCS_OK;
     if (use_mode == FCS_MODE_GEMV) {
         rc = gemv_search(db, q_dev, nq, qlen, mincov, k, qnorm, out_scores, out_ids, out_keys, stream, &launches);
     } else {
-        rc = tc_search(db->tc, q_dev, nq, k, kprime, qnorm, out_scores, out_ids, out_keys, stream, &launches, &fallbacks);
+        const unsigned* flagged = nullptr;
+        rc = tc_search(db->tc, q_dev, nq, k, kprime, qnorm, out_scores, out_ids, out_keys, stream, &launches, &flagged, &fallbacks);
         if (rc != FCS_OK) return fail(rc, "tensor-core search failed: %s", tc_last_error());
+        // queries whose exactness certificate failed (or whose candidate buffer overflowed): exact scan
+        for (int q = 0; q < nq && fallbacks > 0 && rc == FCS_OK; ++q) {
+            if ((flagged[q] & 3u) == 0u) continue;
+            rc = gemv_search(db, q_dev + size_t(q) * DIM, 1, nullptr, 0.f, k, qnorm, out_scores ? out_scores + size_t(q) * k : nullptr,
+                             out_ids ? out_ids + size_t(q) * k : nullptr, out_keys + size_t(q) * k, stream, &launches);
+        }
     }
     if (rc != FCS_OK) return rc;
     FCS_CUDA(cudaEventRecord(db->ev1, stream));
@@ -458,6 +463,19 @@ extern "C" int fcs_search(fcs_db* db, const float* q, int nq, const int32_t* qle
     return FCS_OK;
 }
 
+extern "C" int fcs_debug_tc_approx(fcs_db* db, const float* q, int nq, int qnorm, float* out_scores) {
+    if (!db || !q || !out_scores || nq < 1) return fail(FCS_ERR_INVALID, "fcs_debug_tc_approx: bad argument");
+    if (!db->finalized || !db->tc) return fail(FCS_ERR_STATE, "fcs_debug_tc_approx: needs a finalized database with FCS_DB_KEEP_BF16");
+    DeviceGuard guard(db->device);
+    int rc = ensure_query_bufs(db, size_t(nq), true);
+    if (rc != FCS_OK) return rc;
+    memcpy(db->h_q, q, size_t(nq) * DIM * sizeof(float));
+    FCS_CUDA(cudaMemcpyAsync(db->d_q, db->h_q, size_t(nq) * DIM * sizeof(float), cudaMemcpyHostToDevice, db->stream));
+    rc = tc_debug_approx(db->tc, db->d_q, nq, qnorm, out_scores, db->stream);
+    if (rc != FCS_OK) return fail(rc, "fcs_debug_tc_approx: %s", tc_last_error());
+    return FCS_OK;
+}
+
 extern "C" int fcs_merge_topk(int device, const uint64_t* keys_dev, int n_lists, int nq, int k, float* out_scores_dev,
                               int64_t* out_ids_dev, void* stream) {
     if (!keys_dev) return fail(FCS_ERR_INVALID, "fcs_merge_topk: keys_dev is NULL");
@@ -477,7 +495,8 @@ extern "C" int fcs_get_timing(const fcs_db* db_c, fcs_timing* out) {
         float ms = 0.f;
         FCS_CUDA(cudaEventElapsedTime(&ms, db->ev0, db->ev1));
         db->timing.last_search_ms = ms;
-        db->timing.last_kernel_ms = ms;
+        db->timing.last_kernel_ms = (db->timing.last_mode == FCS_MODE_TC && db->tc) ? tc_last_kernel_ms(db->tc) : ms;
+        db->timing.last_rounds = (db->timing.last_mode == FCS_MODE_TC && db->tc) ? tc_last_rounds(db->tc) : 1;
     }
     *out = db->timing;
     return FCS_OK;

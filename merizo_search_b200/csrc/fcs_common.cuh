@@ -47,6 +47,15 @@ __host__ __device__ __forceinline__ int64_t key_id(uint64_t key) {
     return key == 0 ? int64_t(-1) : int64_t(0xFFFFFFFFu - uint32_t(key));
 }
 
+// --------------------------------------------------------------------------------------
+// Row storage ("row-swizzled fp32"): a row is 32 chunks of 16 B.  Chunk c of local row r is
+// stored at chunk position c ^ (r & 7) of the same row, i.e. the 8 chunks of every aligned
+// 128 B group are permuted by the row's low 3 bits.  A 32-row tile copied verbatim into shared
+// memory can then be read one ROW PER LANE with conflict-free 128-bit loads (8 consecutive lanes
+// hit 8 different 16 B bank groups) -- no cross-lane reduction is needed for the dot product.
+// --------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ int swz_chunk(int chunk, int64_t row) { return chunk ^ int(row & 7); }
+
 #ifdef __CUDACC__
 __device__ __forceinline__ uint64_t shfl_u64(uint64_t v, int src) {
     uint32_t lo = __shfl_sync(FULL, uint32_t(v), src);
@@ -59,12 +68,37 @@ __device__ __forceinline__ uint64_t shfl_up_u64(uint64_t v, int d) {
     return (uint64_t(hi) << 32) | lo;
 }
 
+__device__ __forceinline__ uint64_t shfl_xor_u64(uint64_t v, int m) {
+    uint32_t lo = __shfl_xor_sync(FULL, uint32_t(v), m);
+    uint32_t hi = __shfl_xor_sync(FULL, uint32_t(v >> 32), m);
+    return (uint64_t(hi) << 32) | lo;
+}
+__device__ __forceinline__ uint64_t umax64(uint64_t a, uint64_t b) { return a > b ? a : b; }
+__device__ __forceinline__ uint64_t umin64(uint64_t a, uint64_t b) { return a > b ? b : a; }
+
+// Bitonic sort of 32 keys (one per lane) into descending order by lane: 15 compare-exchange stages.
+__device__ __forceinline__ uint64_t warp_sort_desc(uint64_t v, int lane) {
+#pragma unroll
+    for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+        for (int stride = size >> 1; stride >= 1; stride >>= 1) {
+            const uint64_t o = shfl_xor_u64(v, stride);
+            const bool desc_block = (lane & size) == 0;  // size == 32: always true
+            const bool lower = (lane & stride) == 0;
+            v = (lower == desc_block) ? umax64(v, o) : umin64(v, o);
+        }
+    }
+    return v;
+}
+
 // --------------------------------------------------------------------------------------
 // Warp-resident sorted top-k list.  Rank r (0 = best) lives in lane (r % 32), register
 // slot (r / 32); capacity 32*KPL >= k.  `thr` is the key at rank k-1 (0 while the list
 // holds fewer than k hits): a candidate enters only if its key beats thr, which after a
 // short warm-up is rare (about k*ln(n/k) times over n rows), so the streaming loop pays
-// one compare + one ballot per 32 rows.
+// one compare + one ballot per 32 rows.  One or two entrants are inserted by shifting;
+// more are sorted across the warp and bitonic-merged into the list, and sorted lists are
+// merged the same way (max(A[e], B[n-1-e]) is bitonic and holds the n best of the union).
 // --------------------------------------------------------------------------------------
 template <int KPL>
 struct WarpTopK {
@@ -77,20 +111,15 @@ struct WarpTopK {
         thr = 0;
     }
 
-    // Each lane offers one candidate (cand == 0 -> none).  Warp-uniform control flow.
-    __device__ __forceinline__ void offer(uint64_t cand, int lane, int k) {
-        unsigned m = __ballot_sync(FULL, cand > thr);
-        while (m) {
-            const int src = __ffs(m) - 1;
-            const uint64_t nk = shfl_u64(cand, src);
-            insert(nk, lane, k);
-            m &= m - 1;
-            m &= __ballot_sync(FULL, cand > thr);
-        }
+    __device__ __forceinline__ void update_thr(int k) {
+        const int slot = (k - 1) >> 5;
+        uint64_t sel = key[0];
+#pragma unroll
+        for (int j = 1; j < KPL; ++j) sel = (slot == j) ? key[j] : sel;
+        thr = shfl_u64(sel, (k - 1) & 31);
     }
 
-    // All 32 lanes call with the same nk.  Inserts nk at its sorted position; the last rank falls
-    // off.  The runtime (k-1)>>5 register index is resolved by a small unrolled select.
+    // All 32 lanes call with the same nk.  Inserts nk at its sorted position; the last rank falls off.
     __device__ __forceinline__ void insert(uint64_t nk, int lane, int k) {
         int p = 0;
 #pragma unroll
@@ -105,19 +134,80 @@ struct WarpTopK {
             const int r = j * 32 + lane;
             key[j] = (r > p) ? up : ((r == p) ? nk : key[j]);
         }
-        const int slot = (k - 1) >> 5;
-        uint64_t sel = key[0];
-#pragma unroll
-        for (int j = 1; j < KPL; ++j) sel = (slot == j) ? key[j] : sel;
-        thr = shfl_u64(sel, (k - 1) & 31);
+        update_thr(k);
     }
 
-    // rank r -> key (r in [0, 32*KPL)); caller picks lane/slot: helper to store the first k ranks
+    // Merge a descending-sorted list (same rank layout; slots >= n_slots are empty) into this one.
+    template <int OSLOTS>
+    __device__ __forceinline__ void merge_sorted(const uint64_t (&other)[OSLOTS], int lane, int k) {
+        static_assert(OSLOTS <= KPL, "other list larger than this one");
+        // C[e] = max(A[e], B[n-1-e]); B's slot (KPL-1-j) is empty for KPL-1-j >= OSLOTS
+#pragma unroll
+        for (int j = 0; j < KPL; ++j) {
+            if (KPL - 1 - j < OSLOTS) {
+                const uint64_t rev = shfl_u64(other[KPL - 1 - j], 31 - lane);
+                key[j] = umax64(key[j], rev);
+            }
+        }
+        // bitonic merge, descending, over n = 32*KPL elements; strides >= 32 are register-to-register
+#pragma unroll
+        for (int sj = KPL / 2; sj >= 1; sj >>= 1) {
+#pragma unroll
+            for (int j = 0; j < KPL; ++j) {
+                if ((j & sj) == 0) {
+                    const uint64_t a = key[j], b = key[j + sj];
+                    key[j] = umax64(a, b);
+                    key[j + sj] = umin64(a, b);
+                }
+            }
+        }
+#pragma unroll
+        for (int stride = 16; stride >= 1; stride >>= 1) {
+#pragma unroll
+            for (int j = 0; j < KPL; ++j) {
+                const uint64_t o = shfl_xor_u64(key[j], stride);
+                key[j] = ((lane & stride) == 0) ? umax64(key[j], o) : umin64(key[j], o);
+            }
+        }
+        update_thr(k);
+    }
+
+    // Each lane offers one candidate (cand == 0 -> none).  Warp-uniform control flow.
+    __device__ __forceinline__ void offer(uint64_t cand, int lane, int k) {
+        unsigned m = __ballot_sync(FULL, cand > thr);
+        if (m == 0) return;
+        if (__popc(m) <= 2) {
+            while (m) {
+                const int src = __ffs(m) - 1;
+                const uint64_t nk = shfl_u64(cand, src);
+                insert(nk, lane, k);
+                m &= m - 1;
+                m &= __ballot_sync(FULL, cand > thr);
+            }
+        } else {
+            uint64_t one[1];
+            one[0] = warp_sort_desc(cand > thr ? cand : 0ull, lane);
+            merge_sorted<1>(one, lane, k);
+        }
+    }
+
+    // store the first k ranks
     __device__ __forceinline__ void store(uint64_t* dst, int lane, int k) const {
 #pragma unroll
         for (int j = 0; j < KPL; ++j) {
             const int r = j * 32 + lane;
             if (r < k) dst[r] = key[j];
+        }
+    }
+    // load a stored list of k ranks (ranks >= k read as empty); CG: bypass L1 (data written by other CTAs)
+    template <bool CG>
+    __device__ __forceinline__ void load(const uint64_t* src, int lane, int k) {
+#pragma unroll
+        for (int j = 0; j < KPL; ++j) {
+            const int r = j * 32 + lane;
+            uint64_t v = 0;
+            if (r < k) v = CG ? __ldcg(reinterpret_cast<const unsigned long long*>(src + r)) : src[r];
+            key[j] = v;
         }
     }
 };
@@ -164,6 +254,13 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
             smem_u32(dst_smem)),
         "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(cache_policy)
         : "memory");
+}
+// named barriers (id 1..15): arrive does not block, sync does
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 __device__ __forceinline__ uint64_t policy_evict_first() {
     uint64_t p;

@@ -9,13 +9,13 @@
 namespace fcs {
 
 // ------------------------------------------------------------------ GEMV path (fcs_gemv.cu)
-constexpr int GEMV_MAX_NQ = 4;     // queries scored per DB pass by one launch
+constexpr int GEMV_MAX_NQ = 8;     // queries scored per DB pass by one launch
 constexpr int GEMV_MAX_K = 128;    // k per launch (register-resident lists); larger k = several passes
 constexpr int GEMV_WARPS = 11;     // consumer warps == ring stages
 constexpr int GEMV_STAGE_ROWS = 32;
 
 struct GemvParams {
-    const float* rows;      // [n_rows,128] fp32 (normalised when the flavour asks for it)
+    const float* rows;      // [n_rows,128] fp32, row-swizzled (fcs_common.cuh), normalised when the flavour asks for it
     const uint16_t* lens;   // [n_rows] domain lengths or nullptr
     int64_t n_rows;
     uint32_t id_base;       // global id of row 0
@@ -29,7 +29,7 @@ struct GemvParams {
     int out_stride;         // row pitch of the output arrays (total k of the call)
     int out_off;            // first output rank written by this pass
     int bounded;            // 1: only keys < out_keys[q*out_stride + out_off - 1] may enter (pass >= 2)
-    uint64_t* scratch;      // [grid][nq][k]
+    uint64_t* scratch;      // [nq][grid][k]
     unsigned* ticket;       // last-block-done counter (self-resetting)
     uint64_t* out_keys;     // [nq][out_stride]
     float* out_scores;      // [nq][out_stride] or nullptr
@@ -42,8 +42,8 @@ cudaError_t gemv_launch(const GemvParams& p, int sm_count, cudaStream_t stream);
 cudaError_t gemv_configure();  // one-time cudaFuncSetAttribute for every instantiation
 
 // ------------------------------------------------------------------ loader kernels (fcs_loader.cu)
-cudaError_t normalise_rows_launch(float* rows, int64_t n_rows, float eps, cudaStream_t stream);
-cudaError_t rows_to_bf16_launch(const float* rows, void* rows_bf16, int64_t n_rows, cudaStream_t stream);
+// in place: (optionally) divide each row by max(|row|, eps), then store it chunk-swizzled (fcs_common.cuh)
+cudaError_t finalize_rows_launch(float* rows, int64_t n_rows, int normalise, float eps, cudaStream_t stream);
 // int32 -> u16 with range check; *bad_flag (device int) is set to 1 if any length is outside [0, 65535]
 cudaError_t lengths_to_u16_launch(const int32_t* lens, uint16_t* out, int64_t n, int* bad_flag, cudaStream_t stream);
 

@@ -4,10 +4,9 @@
 // re-normalises the whole [N,128] matrix per call; here each row of a `.pt`-flavour database is
 // divided by max(|row|, 1e-8) once at load (read_database, dbsearch.py:48-64).  faiss-flavour
 // databases are stored pre-normalised (dbutil.py:28-30, "..._raw_128d_norm.db") and are kept as is.
-// Also: the bf16 copy used by the tcgen05 path, and int32 -> u16 domain lengths for the coverage mask.
-// All three are pure streaming kernels (HBM-bound, one warp per row, 128-bit accesses).
-#include <cuda_bf16.h>
-
+// The same pass stores every row chunk-swizzled (fcs_common.cuh) so the scan kernel can read one row
+// per lane without bank conflicts.  Also: int32 -> u16 domain lengths for the coverage mask.
+// Pure streaming kernels (HBM-bound, one warp per row, 128-bit accesses).
 #include "fcs_common.cuh"
 #include "fcs_internal.h"
 
@@ -15,39 +14,22 @@ namespace fcs {
 
 namespace {
 
-__global__ void __launch_bounds__(256) normalise_rows_kernel(float* __restrict__ rows, int64_t n_rows, float eps) {
+__global__ void __launch_bounds__(256) finalize_rows_kernel(float* __restrict__ rows, int64_t n_rows, int normalise, float eps) {
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
     for (int64_t r = warp0; r < n_rows; r += nwarps) {
         float4* row = reinterpret_cast<float4*>(rows + r * DIM);
-        float4 v = row[lane];
-        float ss = v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+        float4 v = row[lane];  // logical chunk `lane`
+        if (normalise) {
+            float ss = v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
 #pragma unroll
-        for (int o = 16; o >= 1; o >>= 1) ss += __shfl_xor_sync(FULL, ss, o);
-        const float d = fmaxf(sqrtf(ss), eps);
-        v.x = v.x / d; v.y = v.y / d; v.z = v.z / d; v.w = v.w / d;
-        row[lane] = v;
-    }
-}
-
-__global__ void __launch_bounds__(256) rows_to_bf16_kernel(const float* __restrict__ rows, __nv_bfloat16* __restrict__ out,
-                                                           int64_t n_vec8) {
-    // one thread converts 8 consecutive floats (two 16 B loads -> one 16 B store)
-    const int64_t stride = int64_t(gridDim.x) * blockDim.x;
-    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n_vec8; i += stride) {
-        const float4 a = reinterpret_cast<const float4*>(rows)[2 * i];
-        const float4 b = reinterpret_cast<const float4*>(rows)[2 * i + 1];
-        __nv_bfloat162 p0 = __floats2bfloat162_rn(a.x, a.y);
-        __nv_bfloat162 p1 = __floats2bfloat162_rn(a.z, a.w);
-        __nv_bfloat162 p2 = __floats2bfloat162_rn(b.x, b.y);
-        __nv_bfloat162 p3 = __floats2bfloat162_rn(b.z, b.w);
-        uint4 o;
-        o.x = *reinterpret_cast<uint32_t*>(&p0);
-        o.y = *reinterpret_cast<uint32_t*>(&p1);
-        o.z = *reinterpret_cast<uint32_t*>(&p2);
-        o.w = *reinterpret_cast<uint32_t*>(&p3);
-        reinterpret_cast<uint4*>(out)[i] = o;
+            for (int o = 16; o >= 1; o >>= 1) ss += __shfl_xor_sync(FULL, ss, o);
+            const float d = fmaxf(sqrtf(ss), eps);
+            v.x = v.x / d; v.y = v.y / d; v.z = v.z / d; v.w = v.w / d;
+        }
+        __syncwarp();  // every lane has read its chunk before any lane overwrites one
+        row[swz_chunk(lane, r)] = v;
     }
 }
 
@@ -69,17 +51,9 @@ inline int grid_for(int64_t work_items, int per_block, int cap) {
 
 }  // namespace
 
-cudaError_t normalise_rows_launch(float* rows, int64_t n_rows, float eps, cudaStream_t stream) {
+cudaError_t finalize_rows_launch(float* rows, int64_t n_rows, int normalise, float eps, cudaStream_t stream) {
     if (n_rows <= 0) return cudaSuccess;
-    normalise_rows_kernel<<<grid_for(n_rows, 8, 148 * 16), 256, 0, stream>>>(rows, n_rows, eps);
-    return cudaGetLastError();
-}
-
-cudaError_t rows_to_bf16_launch(const float* rows, void* rows_bf16, int64_t n_rows, cudaStream_t stream) {
-    if (n_rows <= 0) return cudaSuccess;
-    const int64_t n_vec8 = n_rows * (DIM / 8);
-    rows_to_bf16_kernel<<<grid_for(n_vec8, 256, 148 * 16), 256, 0, stream>>>(
-        rows, reinterpret_cast<__nv_bfloat16*>(rows_bf16), n_vec8);
+    finalize_rows_kernel<<<grid_for(n_rows, 8, 148 * 16), 256, 0, stream>>>(rows, n_rows, normalise, eps);
     return cudaGetLastError();
 }
 

@@ -1,0 +1,203 @@
+"""Host-side search engines over libfcsearch handles.
+
+* ``shard_ranges``      -- contiguous row partition: shard g of G holds rows
+  ``[g*ceil(N/G), min(N,(g+1)*ceil(N/G)))``; global id = local id + offset (the reference's
+  ``I += i0``, dbsearch.py:238).
+* ``LocalEngine``       -- ONE process driving one handle per visible GPU (what the CLI user of
+  ``merizo.py search -d cuda`` gets): queries replicated, shards searched concurrently (one host
+  thread per device; ctypes drops the GIL), per-shard key lists copied peer-to-peer to the first
+  device and merged there by ``fcs_merge_topk``.
+* ``DistributedEngine`` -- one process PER GPU under torchrun: each rank owns one shard; the
+  per-rank ``[nq,k]`` packed key lists are exchanged with a single NCCL all-gather (8 bytes per
+  entry over NVLink) and merged on every rank by the same kernel.  The key exchange is the only
+  collective on the path.
+
+torch is used for device memory, streams and torch.distributed only.
+"""
+from __future__ import annotations
+
+from concurrent.futures import ThreadPoolExecutor
+from typing import Callable, Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import native
+
+DIM = native.DIM
+
+
+def shard_ranges(n_rows: int, n_shards: int) -> List[Tuple[int, int]]:
+    """Contiguous row ranges; trailing shards may be empty when n_rows < n_shards."""
+    if n_rows < 0 or n_shards < 1:
+        raise ValueError("n_rows >= 0 and n_shards >= 1 required")
+    per = -(-n_rows // n_shards) if n_rows else 0
+    return [(min(n_rows, g * per), min(n_rows, (g + 1) * per)) for g in range(n_shards)]
+
+
+def merge_keys_host(keys: np.ndarray, k: int) -> Tuple[np.ndarray, np.ndarray]:
+    """Reference merge of packed key lists on the host: keys [n_lists, nq, k] -> (scores, ids).
+
+    Used only by the CPU (gloo) tests of the multi-rank plumbing and as documentation of the key
+    format: high 32 bits = order-preserving image of the fp32 score, low 32 bits = 0xFFFFFFFF - id.
+    """
+    keys = np.asarray(keys, dtype=np.uint64)
+    n_lists, nq, kk = keys.shape
+    flat = np.transpose(keys, (1, 0, 2)).reshape(nq, n_lists * kk)
+    top = np.sort(flat, axis=1)[:, ::-1][:, :k]  # descending, unsigned
+    return decode_keys(top)
+
+
+def encode_keys(scores: np.ndarray, ids: np.ndarray) -> np.ndarray:
+    s = np.ascontiguousarray(scores, dtype=np.float32).view(np.uint32).astype(np.uint64)
+    neg = (s & np.uint64(0x80000000)) != 0
+    ordered = np.where(neg, (~s) & np.uint64(0xFFFFFFFF), s | np.uint64(0x80000000))
+    ids = np.asarray(ids, dtype=np.int64)
+    key = (ordered << np.uint64(32)) | (np.uint64(0xFFFFFFFF) - ids.astype(np.uint64))
+    return np.where(ids < 0, np.uint64(0), key)
+
+
+def decode_keys(keys: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+    keys = np.asarray(keys, dtype=np.uint64)
+    hi = (keys >> np.uint64(32)).astype(np.uint32)
+    bits = np.where(hi & np.uint32(0x80000000), hi & np.uint32(0x7FFFFFFF), ~hi).astype(np.uint32)
+    scores = bits.view(np.float32).copy()
+    ids = (np.uint64(0xFFFFFFFF) - (keys & np.uint64(0xFFFFFFFF))).astype(np.int64)
+    empty = keys == 0
+    scores[empty] = -np.inf
+    ids[empty] = -1
+    return scores, ids
+
+
+class LocalEngine:
+    """All visible GPUs (or ``devices``) from one process.  Rows are fed block by block."""
+
+    def __init__(self, n_rows: int, devices: Optional[Sequence[int]] = None, normalise_rows: bool = False,
+                 keep_bf16: bool = False, has_lengths: bool = False):
+        if devices is None:
+            devices = list(range(native.device_count()))
+        if len(devices) == 0:
+            raise native.FcsError(native.ERR_CUDA, "no CUDA device visible")
+        # never more shards than 64-row tiles: tiny databases stay on one GPU
+        max_shards = max(1, n_rows // 4096)
+        devices = list(devices)[:max_shards]
+        self.n_rows = int(n_rows)
+        self.devices = devices
+        self.ranges = shard_ranges(self.n_rows, len(devices))
+        self.has_lengths = has_lengths
+        self.shards: List[native.Database] = []
+        for dev, (r0, r1) in zip(devices, self.ranges):
+            self.shards.append(native.Database(r1 - r0, device=dev, id_offset=r0, normalise_rows=normalise_rows,
+                                               keep_bf16=keep_bf16, has_lengths=has_lengths))
+        self._pool = ThreadPoolExecutor(max_workers=len(devices)) if len(devices) > 1 else None
+        self._finalized = False
+
+    # -- loading -----------------------------------------------------------------------------
+    def upload(self, row0: int, rows: np.ndarray, lengths: Optional[np.ndarray] = None) -> None:
+        """Rows [row0, row0+len(rows)) of the GLOBAL matrix; split across the shards that own them."""
+        n = rows.shape[0]
+        for sh, (r0, r1) in zip(self.shards, self.ranges):
+            lo, hi = max(row0, r0), min(row0 + n, r1)
+            if lo < hi:
+                sh.upload(lo - r0, rows[lo - row0:hi - row0], None if lengths is None else lengths[lo - row0:hi - row0])
+
+    def upload_blocks(self, blocks: Iterable[np.ndarray], lengths: Optional[np.ndarray] = None,
+                      progress: Optional[Callable[[int], None]] = None) -> None:
+        """Consume a row-block iterator once (the reference's db_iterator, dbutil.py:33-35)."""
+        i0 = 0
+        for xb in blocks:
+            self.upload(i0, np.asarray(xb), None if lengths is None else lengths[i0:i0 + xb.shape[0]])
+            i0 += xb.shape[0]
+            if progress:
+                progress(i0)
+        if i0 != self.n_rows:
+            raise native.FcsError(native.ERR_INVALID, f"iterator yielded {i0} rows, database has {self.n_rows}")
+
+    def finalize(self) -> None:
+        for sh in self.shards:
+            sh.finalize()
+        self._finalized = True
+
+    # -- search ------------------------------------------------------------------------------
+    def search(self, q: np.ndarray, k: int, qlen: Optional[np.ndarray] = None, mincov: float = 0.0,
+               qnorm: int = native.QNORM_NONE, mode: int = native.MODE_AUTO, kprime: int = 0):
+        """(scores f32 [nq,k], ids i64 [nq,k]) as host arrays; exact; global ids."""
+        q = np.ascontiguousarray(q, dtype=np.float32).reshape(-1, DIM)
+        if len(self.shards) == 1:
+            return self.shards[0].search(q, k, qlen=qlen, mincov=mincov, qnorm=qnorm, mode=mode, kprime=kprime)
+        futs = [self._pool.submit(sh.search, q, k, qlen, mincov, qnorm, mode, kprime) for sh in self.shards]
+        parts = [f.result() for f in futs]
+        keys = np.stack([encode_keys(s, i) for s, i in parts])  # [G, nq, k]
+        return self._merge(keys, k)
+
+    def _merge(self, keys: np.ndarray, k: int):
+        import torch
+
+        dev = torch.device("cuda", self.devices[0])
+        g, nq, _ = keys.shape
+        kd = torch.from_numpy(keys.view(np.int64)).to(dev)
+        sc = torch.empty((nq, k), dtype=torch.float32, device=dev)
+        ids = torch.empty((nq, k), dtype=torch.int64, device=dev)
+        st = torch.cuda.current_stream(dev)
+        native.merge_topk(self.devices[0], kd.data_ptr(), g, nq, k, sc.data_ptr(), ids.data_ptr(), stream=st.cuda_stream)
+        st.synchronize()
+        return sc.cpu().numpy(), ids.cpu().numpy()
+
+    def close(self) -> None:
+        for sh in self.shards:
+            sh.close()
+        if self._pool:
+            self._pool.shutdown(wait=False)
+        self.shards = []
+
+    def __len__(self) -> int:
+        return self.n_rows
+
+
+class DistributedEngine:
+    """One rank per GPU (torchrun).  ``local_search`` and ``merge`` are injectable so that the rank
+    plumbing (partition, offsets, all-gather layout) is testable on CPU with the gloo backend."""
+
+    def __init__(self, n_rows_global: int, rank: Optional[int] = None, world_size: Optional[int] = None,
+                 device: Optional[int] = None, normalise_rows: bool = False, keep_bf16: bool = False,
+                 has_lengths: bool = False, create_handle: bool = True):
+        import torch.distributed as dist
+
+        self.rank = dist.get_rank() if rank is None else rank
+        self.world = dist.get_world_size() if world_size is None else world_size
+        self.n_rows_global = int(n_rows_global)
+        self.ranges = shard_ranges(self.n_rows_global, self.world)
+        self.row0, self.row1 = self.ranges[self.rank]
+        self.device = device
+        self.db: Optional[native.Database] = None
+        if create_handle:
+            self.db = native.Database(self.row1 - self.row0, device=device or 0, id_offset=self.row0,
+                                      normalise_rows=normalise_rows, keep_bf16=keep_bf16, has_lengths=has_lengths)
+
+    def local_keys(self, q_dev, nq: int, k: int, **kw):
+        """This rank's [nq,k] packed keys (torch int64 CUDA tensor viewing uint64 keys)."""
+        import torch
+
+        dev = torch.device("cuda", self.device or 0)
+        keys = torch.empty((nq, k), dtype=torch.int64, device=dev)
+        st = torch.cuda.current_stream(dev)
+        self.db.search_device(q_dev.data_ptr(), nq, k, 0, 0, out_keys_ptr=keys.data_ptr(), stream=st.cuda_stream, **kw)
+        return keys
+
+    def search(self, q_dev, k: int, local_search=None, merge=None, **kw):
+        """Replicated queries in, identical (scores, ids) on every rank out (torch tensors)."""
+        import torch
+        import torch.distributed as dist
+
+        nq = q_dev.shape[0]
+        keys = local_search(q_dev, nq, k) if local_search else self.local_keys(q_dev, nq, k, **kw)
+        gathered = torch.empty((self.world, nq, k), dtype=keys.dtype, device=keys.device)
+        # the one collective on the path: 8 B per entry (flat [world*nq, k] view: the layout gloo and nccl both accept)
+        dist.all_gather_into_tensor(gathered.view(self.world * nq, k), keys)
+        if merge:
+            return merge(gathered, k)
+        sc = torch.empty((nq, k), dtype=torch.float32, device=keys.device)
+        ids = torch.empty((nq, k), dtype=torch.int64, device=keys.device)
+        st = torch.cuda.current_stream(keys.device)
+        native.merge_topk(self.device or 0, gathered.data_ptr(), self.world, nq, k, sc.data_ptr(), ids.data_ptr(),
+                          stream=st.cuda_stream)
+        return sc, ids

@@ -25,7 +25,7 @@ MODE_AUTO, MODE_GEMV, MODE_TC = 0, 1, 2
 EXPORTS = [
     "fcs_version", "fcs_last_error", "fcs_device_count", "fcs_db_create", "fcs_db_upload",
     "fcs_db_upload_device", "fcs_db_finalize", "fcs_db_get_info", "fcs_db_destroy", "fcs_search",
-    "fcs_search_device", "fcs_merge_topk", "fcs_get_timing",
+    "fcs_search_device", "fcs_merge_topk", "fcs_get_timing", "fcs_debug_tc_approx",
 ]
 
 
@@ -37,7 +37,7 @@ class FcsError(RuntimeError):
 
 class Timing(C.Structure):
     _fields_ = [("last_search_ms", C.c_float), ("last_kernel_ms", C.c_float), ("last_mode", C.c_int32),
-                ("last_launches", C.c_int32), ("last_tc_fallbacks", C.c_int32), ("reserved", C.c_int32)]
+                ("last_launches", C.c_int32), ("last_tc_fallbacks", C.c_int32), ("last_rounds", C.c_int32)]
 
 
 class Info(C.Structure):
@@ -81,6 +81,7 @@ def load() -> C.CDLL:
     lib.fcs_search_device.argtypes = [vp, vp, i32, vp, f32, i32, i32, i32, i32, vp, vp, vp, vp]
     lib.fcs_merge_topk.argtypes = [i32, vp, i32, i32, i32, vp, vp, vp]
     lib.fcs_get_timing.argtypes = [vp, C.POINTER(Timing)]
+    lib.fcs_debug_tc_approx.argtypes = [vp, vp, i32, i32, vp]
     for name in EXPORTS:
         if name not in ("fcs_last_error",):
             getattr(lib, name).restype = C.c_int
@@ -158,6 +159,13 @@ class Database:
             self._h, C.c_void_p(q_ptr), int(nq), _np_ptr(ql), float(mincov), int(k), int(qnorm), int(mode), int(kprime),
             C.c_void_p(out_scores_ptr) if out_scores_ptr else None, C.c_void_p(out_ids_ptr) if out_ids_ptr else None,
             C.c_void_p(out_keys_ptr) if out_keys_ptr else None, C.c_void_p(stream) if stream else None))
+
+    def debug_tc_approx(self, q: np.ndarray, qnorm: int = QNORM_NONE) -> np.ndarray:
+        """Test hook: bf16 tensor-core scores [nq, n_rows] (shards of <= 4096 rows)."""
+        q = np.ascontiguousarray(q, dtype=np.float32).reshape(-1, DIM)
+        out = np.empty((q.shape[0], self.n_rows), dtype=np.float32)
+        _check(self._lib.fcs_debug_tc_approx(self._h, _np_ptr(q), q.shape[0], int(qnorm), _np_ptr(out)))
+        return out
 
     def timing(self) -> Timing:
         t = Timing()

@@ -40,5 +40,5 @@ def run(n, nq, k, iters=50):
     h.close()
 
 if __name__ == "__main__":
-    for n, nq, k in [(500000, 1, 10), (500000, 1, 100), (500000, 2, 10), (500000, 4, 10), (4000000, 1, 10), (4000000, 4, 10), (40000000, 1, 10)]:
+    for n, nq, k in [(500000, 1, 10), (500000, 1, 100), (500000, 2, 10), (500000, 4, 10), (500000, 8, 10), (500000, 8, 100), (4000000, 1, 10), (4000000, 8, 10), (40000000, 1, 10)]:
         run(n, nq, k)

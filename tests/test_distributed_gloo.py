@@ -1,0 +1,60 @@
+"""CPU, world_size 2, gloo: the multi-rank plumbing of DistributedEngine (partition, id offsets, key
+all-gather layout, merge) with the oracle standing in for the per-rank CUDA search."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from merizo_search_b200 import engine, synth
+from oracle import foldclass_oracle as orc
+
+N, NQ, K = 5001, 6, 9
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        db = synth.host_db(N, base_seed=12)
+        q = torch.from_numpy(synth.host_queries(NQ, 12, normalise=True))
+        eng = engine.DistributedEngine(N, create_handle=False)
+        lo, hi = eng.row0, eng.row1
+        assert (lo, hi) == engine.shard_ranges(N, world)[rank]
+
+        def local_search(qt, nq, k):  # oracle on this rank's rows, global ids = local + offset
+            D, I = orc.knn_exact_blockwise(qt.numpy(), orc.db_iterator(db[lo:hi], 1024), k)
+            return torch.from_numpy(engine.encode_keys(D, np.where(I >= 0, I + lo, -1)).view(np.int64))
+
+        def merge(gathered, k):
+            return engine.merge_keys_host(gathered.numpy().view(np.uint64), k)
+
+        s, i = eng.search(q, K, local_search=local_search, merge=merge)
+        np.save(os.path.join(out_dir, f"s{rank}.npy"), s)
+        np.save(os.path.join(out_dir, f"i{rank}.npy"), i)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_two_rank_search_equals_single_shard_oracle(tmp_path):
+    world, port = 2, _free_port()
+    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    db = synth.host_db(N, base_seed=12)
+    q = synth.host_queries(NQ, 12, normalise=True)
+    D, I = orc.knn_exact_blockwise(q, orc.db_iterator(db, 262144), K)
+    full = orc.all_scores_ip(q, db)
+    for rank in range(world):
+        s = np.load(tmp_path / f"s{rank}.npy")
+        i = np.load(tmp_path / f"i{rank}.npy")
+        for r in range(NQ):
+            orc.check_topk(s[r], i[r], D[r], I[r], full[r], tol=1e-6)

@@ -56,7 +56,7 @@ def test_golden_ip_flavour_batches():
         h.upload(r0, db[r0:r0 + 20000])
     h.finalize()
     full = orc.all_scores_ip(z["queries_normalised"], db)
-    for nq in (1, 2, 3, 4, 8):  # exercises the 1/2/4-query instantiations and the group loop
+    for nq in (1, 2, 3, 4, 5, 8):  # exercises the 1/2/4-query instantiations and the group loop
         s, i = h.search(z["queries_raw"][:nq], 10, qnorm=native.QNORM_L2, mode=native.MODE_GEMV)
         for r in range(nq):
             orc.check_topk(s[r], i[r], z["D"][r], z["I"][r], full[r], tol=TOL)

@@ -1,0 +1,118 @@
+"""CPU: host-side logic -- shard partition, packed keys, host merge, faiss-flavour file readers."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from merizo_search_b200 import engine, faiss_driver, synth
+from oracle import foldclass_oracle as orc
+
+
+def test_shard_ranges_cover_and_match_reference_offsets():
+    for n, g in [(10, 3), (365_000_000, 8), (7, 8), (0, 2), (500_000, 1), (4097, 4)]:
+        r = engine.shard_ranges(n, g)
+        assert len(r) == g and r[0][0] == 0 and r[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(r, r[1:]))
+        per = -(-n // g) if n else 0
+        assert all(hi - lo <= per for lo, hi in r)
+    assert engine.shard_ranges(365_000_000, 8)[7] == (319_375_000, 365_000_000)
+
+
+def test_key_roundtrip_and_order():
+    rng = np.random.default_rng(0)
+    s = rng.standard_normal(1000).astype(np.float32)
+    s[:6] = [0.0, -0.0, np.inf, -np.inf, 1e-38, -1e-38]
+    ids = rng.permutation(1000).astype(np.int64)
+    k = engine.encode_keys(s, ids)
+    s2, i2 = engine.decode_keys(k)
+    np.testing.assert_array_equal(s.view(np.uint32), s2.view(np.uint32))
+    np.testing.assert_array_equal(ids, i2)
+    order = np.argsort(-k.astype(np.float64), kind="stable")  # monotone enough for a sanity check on distinct scores
+    assert (np.diff(s[np.argsort(k)[::-1]]) <= 0).all()       # bigger key <=> bigger-or-equal score
+    # ties: lower id wins
+    kk = engine.encode_keys(np.array([0.5, 0.5], np.float32), np.array([7, 3]))
+    assert kk[1] > kk[0]
+    # padding
+    e = engine.encode_keys(np.array([-np.inf], np.float32), np.array([-1]))
+    assert e[0] == 0 and engine.decode_keys(e)[1][0] == -1 and np.isneginf(engine.decode_keys(e)[0][0])
+
+
+def test_host_merge_equals_oracle_topk():
+    db = synth.host_db(9000, base_seed=3)
+    q = synth.host_queries(5, 3, normalise=True)
+    k = 12
+    parts = []
+    for lo, hi in engine.shard_ranges(9000, 4):
+        D, I = orc.knn_exact_blockwise(q, orc.db_iterator(db[lo:hi], 1000), k)
+        parts.append(engine.encode_keys(D, I + lo))
+    s, i = engine.merge_keys_host(np.stack(parts), k)
+    D, I = orc.knn_exact_blockwise(q, orc.db_iterator(db, 262144), k)
+    full = orc.all_scores_ip(q, db)
+    for r in range(5):
+        orc.check_topk(s[r], i[r], D[r], I[r], full[r], tol=1e-6)
+
+
+def test_threshold_hits_matches_reference_flattening():
+    rng = np.random.default_rng(1)
+    D = np.sort(rng.random((6, 5)).astype(np.float32), axis=1)[:, ::-1]
+    I = rng.integers(0, 100, (6, 5))
+    a = faiss_driver.threshold_hits(D, I, 0.5)
+    b = orc.threshold_hits(D, I, 0.5)
+    for x, y in zip(a, b):
+        np.testing.assert_array_equal(x, y)
+
+
+@pytest.fixture
+def tiny_faiss_db(tmp_path):
+    """A database in the reference's .json layout, 50 domains."""
+    n = 50
+    rng = np.random.default_rng(2)
+    emb = synth.host_db(n, base_seed=9)
+    emb.tofile(tmp_path / "t_raw_128d_norm.db")
+    names = [f"AF-P{i:05d}-F1-model_v4_TED{i % 3 + 1:02d}" for i in range(n)]
+    with open(tmp_path / "t_raw_128d.index_names", "wb") as fh:
+        for nm in names:
+            fh.write(nm.ljust(32).encode() + b"\n")
+    seqs = ["".join(rng.choice(list("ACDEFGHIKLMNPQRSTVWY"), size=int(rng.integers(25, 60)))) for _ in range(n)]
+    coords = [rng.standard_normal((len(s), 3)).astype(np.float32) for s in seqs]
+    metas = [json.dumps({"cath": f"1.10.{i}.1"}) for i in range(n)]
+
+    def pack(chunks, stem):
+        off, idx = 0, []
+        with open(tmp_path / f"t_{stem}.db", "wb") as fh:
+            for c in chunks:
+                fh.write(c)
+                idx.append((off, off + len(c)))
+                off += len(c)
+        np.asarray(idx, dtype=np.int64).tofile(tmp_path / f"t_{stem}.index")
+
+    pack([s.encode("ascii") for s in seqs], "seq")
+    pack([c.tobytes() for c in coords], "ca")
+    pack([m.encode("ascii") for m in metas], "metadata")
+    info = {"dbfname_IP": "t_raw_128d_norm.db", "DB_SIZE": n, "DB_DIM": 128, "db_names_f": "t_raw_128d.index_names",
+            "sif": "t_seq.index", "sdf": "t_seq.db", "cif": "t_ca.index", "cdf": "t_ca.db", "mif": "t_metadata.index",
+            "mdf": "t_metadata.db"}
+    with open(tmp_path / "t.json", "w") as fh:
+        json.dump(info, fh)
+    return tmp_path, emb, names, seqs, coords, metas
+
+
+def test_record_files_vectorised_readers(tiny_faiss_db):
+    d, emb, names, seqs, coords, metas = tiny_faiss_db
+    info = faiss_driver.read_dbinfo(str(d / "t.json"))
+    assert info == orc.read_dbinfo(str(d / "t.json"))
+    mm = faiss_driver.embedding_memmap(str(d / info["dbfname_IP"]), info["DB_SIZE"], info["DB_DIM"])
+    np.testing.assert_array_equal(np.asarray(mm), emb)
+    blocks = list(faiss_driver.row_blocks(mm, 16))
+    ref_blocks = list(orc.db_iterator(orc.db_memmap(str(d / info["dbfname_IP"]), (50, 128)), 16))
+    assert [b.shape for b in blocks] == [b.shape for b in ref_blocks] == [(16, 128)] * 3 + [(2, 128)]
+    rec = faiss_driver.RecordFiles(str(d), info)
+    ids = np.array([49, 0, 7, 7, 23])
+    assert rec.names(ids) == [names[i] for i in ids]
+    assert rec.sequences(ids) == [seqs[i] for i in ids]
+    assert rec.metadata(ids) == [metas[i] for i in ids]
+    for got, i in zip(rec.coords(ids), ids):
+        np.testing.assert_array_equal(got, coords[i])
+    assert rec.has_metadata()
