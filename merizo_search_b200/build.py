@@ -26,7 +26,7 @@ NVCC_FLAGS = [
     "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC",
     "-cudart", "static",
-]
+] + (["-DFCS_TC_TRACE"] if os.environ.get("FCS_TC_TRACE") else [])
 
 
 def _nvcc() -> str:

@@ -208,12 +208,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemv_topk_kernel(const GemvParams
         const uint64_t* src = p.scratch + size_t(q) * G * k;
         uint64_t* mine = lists + size_t(warp) * k;  // one smem list per warp (12 warps incl. the producer's)
         {
+            // this warp's share of the CTA lists: fetched in chunks with all loads in flight (the lists sit in
+            // L2; one dependent load per list would cost a full L2 round trip each), then merged
             WarpTopK<KPL> a;
             a.init();
-            for (int b = warp; b < G; b += NWARPS + 1) {
-                WarpTopK<KPL> o;
-                o.template load<true>(src + size_t(b) * k, lane, k);
-                a.merge_sorted(o.key, lane, k);
+            constexpr int CH = 16 / KPL;
+            for (int b0 = warp; b0 < G; b0 += CH * (NWARPS + 1)) {
+                WarpTopK<KPL> o[CH];
+#pragma unroll
+                for (int c = 0; c < CH; ++c) {
+                    const int b = b0 + c * (NWARPS + 1);
+                    if (b < G) o[c].template load<true>(src + size_t(b) * k, lane, k);
+                    else o[c].init();
+                }
+#pragma unroll
+                for (int c = 0; c < CH; ++c)
+                    if (b0 + c * (NWARPS + 1) < G) a.merge_sorted(o[c].key, lane, k);
             }
             a.store(mine, lane, k);
         }

@@ -5,22 +5,27 @@
 // large query batches.  A genuine dense contraction S = Q[nq,128] x DB[N,128]^T, so it runs on the
 // 5th-generation tensor cores:
 //
-//   K3  tc_gemm_filter_kernel -- persistent, warp-specialised, one CTA per SM (18 warps):
+//   K3  tc_gemm_filter_kernel -- persistent, warp-specialised, one CTA per SM (19 warps):
 //        * 512 queries (4 tiles of M=128) stay resident in shared memory as bf16 UMMA operand images;
-//          DB rows stream through a 4-stage ring of 64-row bf16 operand images (16 KB each).  Both the
+//          DB rows stream through a 3-stage ring of 128-row bf16 operand images (32 KB each).  Both the
 //          query images and the DB images are stored in HBM already in the canonical K-major
 //          no-swizzle core-matrix layout, so every operand load is ONE contiguous 1-D bulk copy
 //          (cp.async.bulk / UBLKCP, the TMA engine) -- no tensor maps.
-//        * warp 0: TMA producer.  warp 1: issues tcgen05.mma.kind::f16 (M128 x N64 x K16, 8 per tile),
-//          fp32 accumulators in TMEM: 4 query tiles x 2 buffers x 64 columns = all 512 TMEM columns,
-//          so the epilogue of tile-step i overlaps the MMAs of step i+1.
+//        * warp 0: TMA producer.  warps 1-2: one thread each issues tcgen05.mma.kind::f16, M128 x N128 x
+//          K16, 8 per (query tile, DB tile), two query tiles per issuer (a single thread can only issue one
+//          MMA per ~75 cycles; two issuers reach the 64-cycle math rate: scripts/micro/umma_two_issuers.cu).  Measured on B200 (scripts/micro/umma_rate.cu): one tcgen05.mma costs
+//          >= 70 cycles whatever its N, so N=64 caps the tensor pipe at 46 % and N=128 reaches 90 %
+//          (N=256: 100 %); A from TMEM instead of shared memory changes nothing.  Accumulators: fp32 in
+//          TMEM, one 128-column buffer per query tile = all 512 columns; the epilogue of tile t drains
+//          its buffer while the MMAs of the other three tiles run.
 //        * warps 2..17: epilogue, one THREAD PER QUERY (tcgen05.ld 32x32b: lane = accumulator row).
-//          Each thread reduces its 64 scores with 3-input max, compares the group maximum with the
-//          query's current threshold and only on a hit scans the 8-column sub-groups and appends
-//          (score,row) keys to the query's candidate buffer in HBM (atomic slot counter).
+//          Each thread reduces its scores 32 at a time with 3-input max, compares the group maximum
+//          with the query's current threshold and only on a hit scans the 8-column sub-groups and
+//          appends (score,row) keys to the query's candidate buffer in HBM (slots are reserved 8 at a
+//          time with one atomic; the first round, where every row qualifies, indexes by row instead).
 //        The threshold is a per-query constant during a launch; it is the k'-th best approximate
 //        score over the rows seen so far.  The DB is therefore swept in ROUNDS of geometrically
-//        growing size with a tiny selection kernel (tc_select_kernel) in between, which keeps the
+//        growing size with a small selection kernel (tc_select_kernel) in between, which keeps the
 //        number of appends at about k' per round and the epilogue on its fast path.
 //   K4  tc_rescore_kernel -- one warp per query gathers the k' candidate rows (fp32), recomputes the
 //        inner products exactly, keeps the k best, and checks the exactness certificate
@@ -28,6 +33,8 @@
 //        Queries that fail it (or overflowed their buffer) are re-run on the exact fp32 scan (K2).
 #include <cuda_bf16.h>
 
+#include <cstdio>
+#include <cstdlib>
 #include <string>
 
 #include "fcs_common.cuh"
@@ -41,11 +48,14 @@ namespace {
 constexpr int TC_M = 128;                        // queries per UMMA tile
 constexpr int TC_QT = 4;                         // query tiles resident per CTA
 constexpr int TC_QGROUP = TC_M * TC_QT;          // 512
-constexpr int TC_N = 64;                         // DB rows per B tile
+constexpr int TC_N = 128;                        // DB rows per B tile = N of one MMA
 constexpr int A_TILE_BYTES = TC_M * DIM * 2;     // 32 KB
-constexpr int B_TILE_BYTES = TC_N * DIM * 2;     // 16 KB
-constexpr int TC_STAGES = 4;
-constexpr int TC_THREADS = 18 * 32;              // producer + mma + 16 epilogue warps
+constexpr int B_TILE_BYTES = TC_N * DIM * 2;     // 32 KB
+constexpr int TC_STAGES = 3;
+constexpr int TC_PREFETCH = 6;                     // DB tiles prefetched into L2 ahead of the ring
+constexpr int TC_RES = 16;                        // candidate slots reserved per atomic
+constexpr int TC_MMA_WARPS = 2;                   // MMA-issuing warps (one thread each), 2 query tiles apiece
+constexpr int TC_THREADS = (1 + TC_MMA_WARPS + 16) * 32;  // producer + MMA issuers + 16 epilogue warps
 constexpr int TC_CAP = 4096;                     // candidate slots per query
 constexpr int TC_SMEM = TC_QT * A_TILE_BYTES + TC_STAGES * B_TILE_BYTES + 32 * 8 + 16;
 constexpr int TC_MAX_KPRIME = 512;
@@ -85,6 +95,12 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
           "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr)
         : "memory");
+}
+__device__ __forceinline__ void tc_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ float max3(float a, float b, float c) {
@@ -131,7 +147,7 @@ __global__ void __launch_bounds__(128) tc_prep_kernel(const float* __restrict__ 
                                                       float* __restrict__ qn, uint8_t* __restrict__ a_img,
                                                       float* __restrict__ thr, unsigned* __restrict__ cnt,
                                                       unsigned* __restrict__ flags, float* __restrict__ q_norm,
-                                                      unsigned* __restrict__ n_flagged) {
+                                                      unsigned* __restrict__ n_flagged, unsigned first_round_rows) {
     const int lane = threadIdx.x & 31;
     const int q = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (q == 0 && lane == 0) *n_flagged = 0u;
@@ -152,7 +168,7 @@ __global__ void __launch_bounds__(128) tc_prep_kernel(const float* __restrict__ 
         reinterpret_cast<float4*>(qn + size_t(q) * DIM)[lane] = v;
         if (lane == 0) {
             thr[q] = -INFINITY;
-            cnt[q] = 0u;
+            cnt[q] = first_round_rows;  // the first round indexes its candidates by row
             flags[q] = 0u;
             q_norm[q] = nrm;
         }
@@ -177,13 +193,42 @@ struct TcGemmParams {
     int64_t tile0, tile1;  // DB tiles of this round
     const float* thr;      // [nq] approximate-score threshold (strict >)
     unsigned* cnt;         // [nq] append counters
-    uint64_t* cand;        // [nq][TC_CAP] approximate keys (score, LOCAL row)
+    uint64_t* cand;        // [nq][TC_CAP] approximate keys (score, LOCAL row); 0 = unused reserved slot
+    int first_round;       // thresholds are all -inf and tile0 == 0: slot = row, no atomics
+    int trace_on;          // debug builds (FCS_TC_TRACE): record cycle stamps in this launch
 };
 
-__device__ __forceinline__ void tc_append(const TcGemmParams& p, int q, float v, int64_t row) {
-    if (row < p.n_rows) {
-        const unsigned slot = atomicAdd(p.cnt + q, 1u);
-        if (slot < unsigned(TC_CAP)) p.cand[size_t(q) * TC_CAP + slot] = make_key(v, uint32_t(row));
+#ifdef FCS_TC_TRACE
+// debug build only: cycle stamps of CTA 0 (MMA thread: row 0/1; epilogue warp of tile 0, quadrant 2: rows 2..4)
+__device__ long long g_trace[5][256];
+#define TRACE(row, idx, cond) do { if (p.trace_on && (cond) && (idx) < 256) g_trace[row][idx] = clock64(); } while (0)
+#else
+#define TRACE(row, idx, cond) do { } while (0)
+#endif
+
+// Per-thread slot reservation: one atomic buys TC_RES slots of the query's buffer.
+struct SlotRes {
+    unsigned base = 0, used = TC_RES;
+};
+__device__ __forceinline__ void tc_append(const TcGemmParams& p, SlotRes& res, int q, float v, int64_t row) {
+    if (row >= p.n_rows) return;  // zero padding rows of the last DB tile
+    unsigned slot;
+    if (p.first_round) {
+        slot = unsigned(row);
+    } else {
+        if (res.used == TC_RES) {
+            res.base = atomicAdd(p.cnt + q, unsigned(TC_RES));
+            res.used = 0;
+        }
+        slot = res.base + res.used++;
+    }
+    if (slot < unsigned(TC_CAP)) p.cand[size_t(q) * TC_CAP + slot] = make_key(v, uint32_t(row));
+}
+// unused slots of the last reservation must read as empty
+__device__ __forceinline__ void tc_close_reservation(const TcGemmParams& p, SlotRes& res, int q) {
+    for (; res.used < TC_RES; ++res.used) {
+        const unsigned slot = res.base + res.used;
+        if (slot < unsigned(TC_CAP)) p.cand[size_t(q) * TC_CAP + slot] = 0ull;
     }
 }
 
@@ -192,27 +237,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_filter_kernel(const TcG
     uint8_t* sA = smem;
     uint8_t* sB = smem + TC_QT * A_TILE_BYTES;
     uint64_t* bars = reinterpret_cast<uint64_t*>(sB + TC_STAGES * B_TILE_BYTES);
-    uint64_t* full_b = bars;             // [4]
-    uint64_t* empty_b = bars + 4;        // [4]
-    uint64_t* tmem_full = bars + 8;      // [tile*2 + buf]
-    uint64_t* tmem_empty = bars + 16;    // [tile*2 + buf]
-    uint64_t* a_full = bars + 24;
-    uint64_t* a_empty = bars + 25;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 26);
+    uint64_t* full_b = bars;             // [TC_STAGES]
+    uint64_t* empty_b = bars + 4;        // [TC_STAGES]
+    uint64_t* tmem_full = bars + 8;      // [tile]
+    uint64_t* tmem_empty = bars + 12;    // [tile]
+    uint64_t* a_full = bars + 16;
+    uint64_t* a_empty = bars + 17;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     if (tid == 0) {
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < TC_STAGES; ++i) {
             mbar_init(&full_b[i], 1);
-            mbar_init(&empty_b[i], 1);
+            mbar_init(&empty_b[i], TC_MMA_WARPS);
         }
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < TC_QT; ++i) {
             mbar_init(&tmem_full[i], 1);
             mbar_init(&tmem_empty[i], 4);  // the 4 epilogue warps of a query tile
         }
         mbar_init(a_full, 1);
-        mbar_init(a_empty, 1);
+        mbar_init(a_empty, TC_MMA_WARPS);
         mbar_fence_init();
     }
     if (warp == 1) {  // whole warp: TMEM allocation (all 512 columns; one CTA per SM)
@@ -245,6 +290,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_filter_kernel(const TcG
                     bulk_g2s(sA + t * A_TILE_BYTES, p.a_img + (size_t(qg) * TC_QT + t) * A_TILE_BYTES, A_TILE_BYTES, a_full, pol_keep);
                 for (int64_t j = 0; j < seg_len; ++j, ++it) {
                     const uint32_t st = it % TC_STAGES, ph = (it / TC_STAGES) & 1u;
+                    // only 2 stages (64 KB) can be in flight behind the one being consumed: pull tiles further
+                    // ahead into L2 so the bulk copies below see L2 latency, not DRAM latency
+                    if (j + TC_PREFETCH < seg_len)
+                        bulk_prefetch_l2(p.b_img + size_t(p.tile0 + ti + j + TC_PREFETCH) * B_TILE_BYTES, B_TILE_BYTES);
                     mbar_wait(&empty_b[st], ph ^ 1u);
                     mbar_arrive_expect_tx(&full_b[st], B_TILE_BYTES);
                     bulk_g2s(sB + st * B_TILE_BYTES, p.b_img + size_t(p.tile0 + ti + j) * B_TILE_BYTES, B_TILE_BYTES, &full_b[st], pol_stream);
@@ -253,8 +302,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_filter_kernel(const TcG
             }
         }
         __syncwarp();
-    } else if (warp == 1) {
-        // ---------------------------------------------------------------- MMA issuer (one thread)
+    } else if (warp <= TC_MMA_WARPS) {
+        // ---------------------------------------------------------------- MMA issuers (one thread per warp).
+        // One thread can issue a tcgen05.mma only every ~75 cycles (scripts/micro/umma_two_issuers.cu); an
+        // M128 x N128 x K16 MMA is 64 cycles of tensor-pipe work, so two issuers keep the pipe full.
+        const int t_first = (warp - 1) * (TC_QT / TC_MMA_WARPS);
         if (lane == 0) {
             const uint32_t a_addr = smem_u32(sA), b_addr = smem_u32(sB);
             uint32_t it = 0, seg = 0;
@@ -265,23 +317,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_filter_kernel(const TcG
                 tc_fence_after();
                 for (int64_t j = 0; j < seg_len; ++j, ++it) {
                     const uint32_t st = it % TC_STAGES, ph = (it / TC_STAGES) & 1u;
-                    const uint32_t buf = it & 1u, tph = (it >> 1) & 1u;
+                    const uint32_t tph = it & 1u;
                     mbar_wait(&full_b[st], ph);
                     tc_fence_after();
 #pragma unroll
-                    for (int t = 0; t < TC_QT; ++t) {
-                        mbar_wait(&tmem_empty[t * 2 + buf], tph ^ 1u);  // epilogue has drained this accumulator
+                    for (int tt = 0; tt < TC_QT / TC_MMA_WARPS; ++tt) {
+                        const int t = t_first + tt;
+                        mbar_wait(&tmem_empty[t], tph ^ 1u);  // epilogue has drained this tile's accumulator
                         tc_fence_after();
-                        const uint32_t d_tmem = tmem_base + uint32_t((t * 2 + buf) * TC_N);
+                        TRACE(0, it, blockIdx.x == 0 && t == 0);
+                        const uint32_t d_tmem = tmem_base + uint32_t(t * TC_N);
 #pragma unroll
                         for (int k = 0; k < DIM / 16; ++k) {
                             const uint64_t ad = make_desc(a_addr + t * A_TILE_BYTES + k * 256);
                             const uint64_t bd = make_desc(b_addr + st * B_TILE_BYTES + k * 256);
                             tc_mma(d_tmem, ad, bd, k > 0 ? 1u : 0u);
                         }
-                        tc_commit(&tmem_full[t * 2 + buf]);
+                        tc_commit(&tmem_full[t]);
+                        TRACE(1, it, blockIdx.x == 0 && t == 0);
                     }
-                    tc_commit(&empty_b[st]);  // B stage free once these MMAs have read it
+                    tc_commit(&empty_b[st]);  // B stage free once both issuers' MMAs have read it
                 }
                 tc_commit(a_empty);
                 s += seg_len;
@@ -290,48 +345,74 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_filter_kernel(const TcG
         __syncwarp();
     } else {
         // ---------------------------------------------------------------- epilogue: thread = query
-        const int t = (warp - 2) >> 2;  // query tile
+        const int t = (warp - 1 - TC_MMA_WARPS) >> 2;  // query tile (4 consecutive warps cover the 4 lane quadrants)
         const int quad = warp & 3;      // TMEM lane quadrant this warp may access
+        const uint32_t lane_base = uint32_t(quad * 32) << 16;
         uint32_t it = 0;
         for (int64_t s = s_begin; s < s_end;) {
             const int64_t qg = s / n_tiles, ti = s - qg * n_tiles;
             const int64_t seg_len = (s_end - s < n_tiles - ti) ? (s_end - s) : (n_tiles - ti);
             const int q = int(qg) * TC_QGROUP + t * TC_M + quad * 32 + lane;
             const float thr = (q < p.nq) ? p.thr[q] : INFINITY;
+            SlotRes res;
             for (int64_t j = 0; j < seg_len; ++j, ++it) {
-                const uint32_t buf = it & 1u, tph = (it >> 1) & 1u;
-                mbar_wait(&tmem_full[t * 2 + buf], tph);
+                const uint32_t tph = it & 1u;
+                mbar_wait(&tmem_full[t], tph);
                 tc_fence_after();
+                TRACE(2, it, blockIdx.x == 0 && warp == 3 && lane == 0);
                 const int64_t row_base = (p.tile0 + ti + j) * TC_N;
-#pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    uint32_t r[32];
-                    tc_ld32(tmem_base + (uint32_t(quad * 32) << 16) + uint32_t((t * 2 + buf) * TC_N + half * 32), r);
-                    tc_wait_ld();
+                // Fast path: 32 scores per tcgen05.ld, reduced with 3-input max, one compare against the
+                // threshold.  Slow path (some lane of the warp has a hit in an 8-column group): the group is
+                // re-read from TMEM into 8 fixed registers and handled by ONE compact, warp-uniform loop.  Keep
+                // it small: the first version unrolled an append site per column (~140 KB of SASS) and every hit
+                // ran through cold code -- instruction-cache misses cost 3-5 k cycles per append.
+#pragma unroll 1
+                for (int part = 0; part < TC_N / 32; ++part) {
+                    const uint32_t taddr = tmem_base + lane_base + uint32_t(t * TC_N + part * 32);
                     float m[4];
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        const float* f = reinterpret_cast<const float*>(&r[g * 8]);
-                        m[g] = fmaxf(max3(f[0], f[1], f[2]), max3(max3(f[3], f[4], f[5]), f[6], f[7]));
-                    }
-                    const float mx = fmaxf(max3(m[0], m[1], m[2]), m[3]);
-                    if (mx > thr) {  // rare once the threshold is warm
+                    {
+                        uint32_t r[32];
+                        tc_ld32(taddr, r);
+                        tc_wait_ld();
 #pragma unroll
                         for (int g = 0; g < 4; ++g) {
-                            if (m[g] > thr) {
+                            const float* f = reinterpret_cast<const float*>(&r[g * 8]);
+                            m[g] = fmaxf(max3(f[0], f[1], f[2]), max3(max3(f[3], f[4], f[5]), f[6], f[7]));
+                        }
+                    }
+                    const float mx = fmaxf(max3(m[0], m[1], m[2]), m[3]);
+                    if (__any_sync(FULL, p.first_round || mx > thr)) {  // rare once the threshold is warm
+                        unsigned wgm = 0;  // groups in which some lane has a hit (warp-uniform)
 #pragma unroll
-                                for (int c = 0; c < 8; ++c) {
-                                    const float v = __uint_as_float(r[g * 8 + c]);
-                                    if (v > thr) tc_append(p, q, v, row_base + half * 32 + g * 8 + c);
-                                }
+                        for (int g = 0; g < 4; ++g) wgm |= __any_sync(FULL, p.first_round || m[g] > thr) ? (1u << g) : 0u;
+                        while (wgm) {
+                            const int g = __ffs(wgm) - 1;
+                            wgm &= wgm - 1;
+                            uint32_t v8[8];
+                            __syncwarp();  // lanes left the divergent append loop below at different times
+                            tc_ld8(taddr + uint32_t(g * 8), v8);
+                            tc_wait_ld();
+                            unsigned hits = 0;
+#pragma unroll
+                            for (int c = 0; c < 8; ++c) hits |= (p.first_round || __uint_as_float(v8[c]) > thr) ? (1u << c) : 0u;
+                            while (hits) {
+                                const int c = __ffs(hits) - 1;
+                                hits &= hits - 1;
+                                uint32_t bits = v8[0];
+#pragma unroll
+                                for (int cc = 1; cc < 8; ++cc) bits = (c == cc) ? v8[cc] : bits;
+                                tc_append(p, res, q, __uint_as_float(bits), row_base + part * 32 + g * 8 + c);
                             }
                         }
                     }
                 }
+                TRACE(3, it, blockIdx.x == 0 && warp == 3 && lane == 0);
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&tmem_empty[t * 2 + buf]);
+                if (lane == 0) mbar_arrive(&tmem_empty[t]);
+                TRACE(4, it, blockIdx.x == 0 && warp == 3 && lane == 0);
             }
+            if (!p.first_round) tc_close_reservation(p, res, q);
             s += seg_len;
         }
     }
@@ -351,6 +432,7 @@ __global__ void __launch_bounds__(256) tc_select_kernel(uint64_t* __restrict__ c
                                                         float* __restrict__ thr, unsigned* __restrict__ flags,
                                                         unsigned* __restrict__ n_flagged, int kprime) {
     extern __shared__ uint64_t s_keys[];
+    __shared__ int s_valid;
     const int q = blockIdx.x, tid = threadIdx.x;
     const unsigned raw = cnt[q];
     const unsigned fl = flags[q];
@@ -359,15 +441,19 @@ __global__ void __launch_bounds__(256) tc_select_kernel(uint64_t* __restrict__ c
         if (tid == 0 && (atomicOr(flags + q, 1u) & 3u) == 0u) atomicAdd(n_flagged, 1u);
     }
     const int n = int(raw < unsigned(TC_CAP) ? raw : unsigned(TC_CAP));
-    int P = 2;
-    while (P < n) P <<= 1;
+    int P = 2, logP = 1;
+    while (P < n) { P <<= 1; ++logP; }
     uint64_t* base = cand + size_t(q) * TC_CAP;
     for (int i = tid; i < P; i += 256) s_keys[i] = (i < n) ? base[i] : 0ull;
+    if (tid == 0) s_valid = 0;
     __syncthreads();
-    for (int size = 2; size <= P; size <<= 1) {
-        for (int stride = size >> 1; stride >= 1; stride >>= 1) {
+    // bitonic sort, descending; all strides are powers of two
+    for (int ls = 1; ls <= logP; ++ls) {
+        const int size = 1 << ls;
+        for (int lt = ls - 1; lt >= 0; --lt) {
+            const int stride = 1 << lt;
             for (int i = tid; i < (P >> 1); i += 256) {
-                const int lo = ((i / stride) * stride << 1) + (i % stride);
+                const int lo = ((i & ~(stride - 1)) << 1) | (i & (stride - 1));
                 const int hi = lo + stride;
                 const bool desc = (lo & size) == 0;
                 const uint64_t a = s_keys[lo], b = s_keys[hi];
@@ -379,11 +465,16 @@ __global__ void __launch_bounds__(256) tc_select_kernel(uint64_t* __restrict__ c
             __syncthreads();
         }
     }
-    const int keep = n < kprime ? n : kprime;
+    // unused reserved slots hold key 0 and sorted to the end: count the real candidates
+    for (int i = tid; i < P; i += 256)
+        if (s_keys[i] != 0ull && (i + 1 == P || s_keys[i + 1] == 0ull)) s_valid = i + 1;
+    __syncthreads();
+    const int nv = s_valid;
+    const int keep = nv < kprime ? nv : kprime;
     for (int i = tid; i < keep; i += 256) base[i] = s_keys[i];
     if (tid == 0) {
         cnt[q] = unsigned(keep);
-        if (n >= kprime) thr[q] = key_score(s_keys[kprime - 1]);
+        if (nv >= kprime) thr[q] = key_score(s_keys[kprime - 1]);
         flags[q] = (flags[q] & 0xFFu) | 4u | (unsigned(keep) << 8);
     }
 }
@@ -505,6 +596,7 @@ struct TcState {
     unsigned* h_n_flagged = nullptr;  // pinned
     unsigned* h_flags = nullptr;      // pinned, nq_cap
     double growth = 3.0;
+    bool verbose = false;
     // timing of the dominant kernel: one event pair per K3 launch of the last search
     static constexpr int MAX_ROUNDS = 48;
     cudaEvent_t ev[2 * MAX_ROUNDS] = {};
@@ -549,6 +641,7 @@ int tc_create(TcState** out, int device, int sm_count, const float* rows, int64_
     s->n_rows = n_rows;
     s->id_base = id_base;
     s->n_tiles = (n_rows + TC_N - 1) / TC_N;
+    s->verbose = getenv("FCS_TC_VERBOSE") != nullptr;
     if (const char* g = getenv("FCS_TC_GROWTH")) {
         const double v = atof(g);
         if (v >= 1.25 && v <= 16.0) s->growth = v;
@@ -599,7 +692,8 @@ static int tc_ensure_workspace(TcState* s, int nq) {
 }
 
 int tc_default_kprime(int k) {
-    int kp = 2 * k + 32;
+    // margin for the exactness certificate: the bf16 rounding bound eps covers a few dozen ranks at TED scale
+    int kp = k + (k * 6 / 10 > 32 ? k * 6 / 10 : 32);
     kp = (kp + 31) / 32 * 32;
     return kp > TC_MAX_KPRIME ? TC_MAX_KPRIME : kp;
 }
@@ -620,8 +714,11 @@ int tc_search(TcState* s, const float* q_dev, int nq, int k, int kprime, int qno
     const int n_qgroups = (nq + TC_QGROUP - 1) / TC_QGROUP;
     const int nq_pad = n_qgroups * TC_QGROUP;
 
+    // the first round (threshold -inf: every row is a candidate) covers at most CAP/2 rows and indexes by row
+    const int64_t first_tiles = (TC_CAP / 2) / TC_N;
+    const int64_t first_rows = (first_tiles * TC_N < s->n_rows) ? first_tiles * TC_N : s->n_rows;
     tc_prep_kernel<<<(nq_pad + 3) / 4, 128, 0, stream>>>(q_dev, nq, nq_pad, qnorm, s->qn, s->a_img, s->thr, s->cnt, s->flags,
-                                                         s->q_norm, s->n_flagged);
+                                                         s->q_norm, s->n_flagged, unsigned(first_rows));
     TC_CUDA(cudaGetLastError());
     ++*launches;
 
@@ -634,15 +731,16 @@ int tc_search(TcState* s, const float* q_dev, int nq, int k, int kprime, int qno
     gp.thr = s->thr;
     gp.cnt = s->cnt;
     gp.cand = s->cand;
-    // rounds: with threshold -inf every row is appended, so the first round is at most CAP/2 rows;
-    // afterwards a round over R rows appends about k' * R / seen keys per query.
+    // rounds: a round over R rows appends about k' * R / seen keys per query
     int64_t seen = 0;
     int rounds = 0;
-    int64_t round_tiles = (TC_CAP / 2) / TC_N;
+    int64_t round_tiles = first_tiles;
     while (seen < s->n_tiles) {
         const int64_t t1 = (seen + round_tiles < s->n_tiles) ? (seen + round_tiles) : s->n_tiles;
         gp.tile0 = seen;
         gp.tile1 = t1;
+        gp.first_round = rounds == 0 ? 1 : 0;
+        gp.trace_on = (getenv("FCS_TC_TRACE_ROUND") ? atoi(getenv("FCS_TC_TRACE_ROUND")) : 7) == rounds;
         const int64_t steps = int64_t(n_qgroups) * (t1 - seen);
         const int grid = int(steps < s->sm_count ? steps : s->sm_count);
         const bool timed = rounds < TcState::MAX_ROUNDS;
@@ -685,11 +783,22 @@ int tc_search(TcState* s, const float* q_dev, int nq, int k, int kprime, int qno
     // which queries need the exact fallback?  (host decision: one small synchronous read-back)
     TC_CUDA(cudaMemcpyAsync(s->h_n_flagged, s->n_flagged, sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
     TC_CUDA(cudaStreamSynchronize(stream));
+#ifdef FCS_TC_TRACE
+    {
+        static long long h[5][256];
+        cudaMemcpyFromSymbol(h, g_trace, sizeof h);
+        fprintf(stderr, "[fcs_tc trace, last round, CTA 0, cycles relative to first stamp]\n it  mma_ready mma_issued | epi_full epi_done epi_arrived\n");
+        for (int i = 100; i < 116; ++i)
+            fprintf(stderr, "%3d  %9lld %9lld | %9lld %9lld %9lld\n", i, h[0][i] - h[0][100], h[1][i] - h[0][100], h[2][i] - h[0][100],
+                    h[3][i] - h[0][100], h[4][i] - h[0][100]);
+    }
+#endif
     s->last_k3_ms = 0.f;
     s->last_rounds = rounds;
     for (int r = 0; r < rounds && r < TcState::MAX_ROUNDS; ++r) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, s->ev[2 * r], s->ev[2 * r + 1]) == cudaSuccess) s->last_k3_ms += ms;
+        if (s->verbose) fprintf(stderr, "[fcs_tc] round %d: gemm+filter %.3f ms\n", r, ms);
     }
     if (s->h_n_flagged[0] > 0) {
         TC_CUDA(cudaMemcpyAsync(s->h_flags, s->flags, size_t(nq) * 4, cudaMemcpyDeviceToHost, stream));
@@ -712,9 +821,10 @@ int tc_debug_approx(TcState* s, const float* q_dev, int nq, int qnorm, float* ou
     const int n_qgroups = (nq + TC_QGROUP - 1) / TC_QGROUP;
     const int nq_pad = n_qgroups * TC_QGROUP;
     tc_prep_kernel<<<(nq_pad + 3) / 4, 128, 0, stream>>>(q_dev, nq, nq_pad, qnorm, s->qn, s->a_img, s->thr, s->cnt, s->flags,
-                                                         s->q_norm, s->n_flagged);
+                                                         s->q_norm, s->n_flagged, unsigned(s->n_rows));
     TC_CUDA(cudaGetLastError());
     TcGemmParams gp = {};
+    gp.first_round = 1;
     gp.a_img = s->a_img; gp.b_img = s->b_img; gp.n_rows = s->n_rows; gp.nq = nq; gp.n_qgroups = n_qgroups;
     gp.thr = s->thr; gp.cnt = s->cnt; gp.cand = s->cand; gp.tile0 = 0; gp.tile1 = s->n_tiles;
     const int64_t steps = int64_t(n_qgroups) * s->n_tiles;
