@@ -5,27 +5,28 @@
 // large query batches.  A genuine dense contraction S = Q[nq,128] x DB[N,128]^T, so it runs on the
 // 5th-generation tensor cores:
 //
-//   K3  tc_gemm_filter_kernel -- persistent, warp-specialised, one CTA per SM (19 warps):
+//   K3  tc_gemm_filter_kernel -- persistent, warp-specialised, one CTA per SM (21 warps):
 //        * 512 queries (4 tiles of M=128) stay resident in shared memory as bf16 UMMA operand images;
 //          DB rows stream through a 3-stage ring of 128-row bf16 operand images (32 KB each).  Both the
 //          query images and the DB images are stored in HBM already in the canonical K-major
 //          no-swizzle core-matrix layout, so every operand load is ONE contiguous 1-D bulk copy
 //          (cp.async.bulk / UBLKCP, the TMA engine) -- no tensor maps.
-//        * warp 0: TMA producer.  warps 1-2: one thread each issues tcgen05.mma.kind::f16, M128 x N128 x
-//          K16, 8 per (query tile, DB tile), two query tiles per issuer (a single thread can only issue one
-//          MMA per ~75 cycles; two issuers reach the 64-cycle math rate: scripts/micro/umma_two_issuers.cu).  Measured on B200 (scripts/micro/umma_rate.cu): one tcgen05.mma costs
+//        * warp 0: TMA producer.  warps 1-4: one thread each issues tcgen05.mma.kind::f16, M128 x N128 x
+//          K16, 8 per (query tile, DB tile), one query tile per issuer (a single thread can only issue one
+//          MMA per ~75 cycles; two or more issuers reach the 64-cycle math rate, scripts/micro/
+//          umma_two_issuers.cu, and one issuer per tile keeps a slow epilogue from stalling the other tiles).  Measured on B200 (scripts/micro/umma_rate.cu): one tcgen05.mma costs
 //          >= 70 cycles whatever its N, so N=64 caps the tensor pipe at 46 % and N=128 reaches 90 %
 //          (N=256: 100 %); A from TMEM instead of shared memory changes nothing.  Accumulators: fp32 in
 //          TMEM, one 128-column buffer per query tile = all 512 columns; the epilogue of tile t drains
 //          its buffer while the MMAs of the other three tiles run.
-//        * warps 2..17: epilogue, one THREAD PER QUERY (tcgen05.ld 32x32b: lane = accumulator row).
+//        * warps 5..20: epilogue, one THREAD PER QUERY (tcgen05.ld 32x32b: lane = accumulator row).
 //          Each thread reduces its scores 32 at a time with 3-input max, compares the group maximum
 //          with the query's current threshold and only on a hit scans the 8-column sub-groups and
 //          appends (score,row) keys to the query's candidate buffer in HBM (slots are reserved 8 at a
 //          time with one atomic; the first round, where every row qualifies, indexes by row instead).
 //        The threshold is a per-query constant during a launch; it is the k'-th best approximate
 //        score over the rows seen so far.  The DB is therefore swept in ROUNDS of geometrically
-//        growing size with a small selection kernel (tc_select_kernel) in between, which keeps the
+//        growing size with a small selection kernel (tc_select_warp_kernel) in between, which keeps the
 //        number of appends at about k' per round and the epilogue on its fast path.
 //   K4  tc_rescore_kernel -- one warp per query gathers the k' candidate rows (fp32), recomputes the
 //        inner products exactly, keeps the k best, and checks the exactness certificate
@@ -54,7 +55,7 @@ constexpr int B_TILE_BYTES = TC_N * DIM * 2;     // 32 KB
 constexpr int TC_STAGES = 3;
 constexpr int TC_PREFETCH = 6;                     // DB tiles prefetched into L2 ahead of the ring
 constexpr int TC_RES = 16;                        // candidate slots reserved per atomic
-constexpr int TC_MMA_WARPS = 2;                   // MMA-issuing warps (one thread each), 2 query tiles apiece
+constexpr int TC_MMA_WARPS = 4;                   // MMA-issuing warps (one thread each), one query tile apiece
 constexpr int TC_THREADS = (1 + TC_MMA_WARPS + 16) * 32;  // producer + MMA issuers + 16 epilogue warps
 constexpr int TC_CAP = 4096;                     // candidate slots per query
 constexpr int TC_SMEM = TC_QT * A_TILE_BYTES + TC_STAGES * B_TILE_BYTES + 32 * 8 + 16;
@@ -359,7 +360,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_filter_kernel(const TcG
                 const uint32_t tph = it & 1u;
                 mbar_wait(&tmem_full[t], tph);
                 tc_fence_after();
-                TRACE(2, it, blockIdx.x == 0 && warp == 3 && lane == 0);
+                TRACE(2, it, blockIdx.x == 0 && warp == 5 && lane == 0);
                 const int64_t row_base = (p.tile0 + ti + j) * TC_N;
                 // Fast path: 32 scores per tcgen05.ld, reduced with 3-input max, one compare against the
                 // threshold.  Slow path (some lane of the warp has a hit in an 8-column group): the group is
@@ -406,11 +407,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_filter_kernel(const TcG
                         }
                     }
                 }
-                TRACE(3, it, blockIdx.x == 0 && warp == 3 && lane == 0);
+                TRACE(3, it, blockIdx.x == 0 && warp == 5 && lane == 0);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tmem_empty[t]);
-                TRACE(4, it, blockIdx.x == 0 && warp == 3 && lane == 0);
+                TRACE(4, it, blockIdx.x == 0 && warp == 5 && lane == 0);
             }
             if (!p.first_round) tc_close_reservation(p, res, q);
             s += seg_len;
@@ -428,6 +429,71 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_filter_kernel(const TcG
 // ------------------------------------------------------------------------------------------------
 // between rounds: keep each query's k' best candidates (sorted), publish the k'-th score as threshold
 // ------------------------------------------------------------------------------------------------
+// Fast path of the selection: one WARP per query, candidates in registers (<= 32 per lane), the k'-th largest
+// score found by bisection on the 32-bit order-preserving score word (32 vote rounds), survivors compacted to the
+// front of the buffer.  No sort: the rounds only need the k' best as a set and the k'-th score as threshold.
+constexpr int SEL_WARP_MAX = 1024;
+__global__ void __launch_bounds__(128) tc_select_warp_kernel(uint64_t* __restrict__ cand, unsigned* __restrict__ cnt,
+                                                             float* __restrict__ thr, unsigned* __restrict__ flags, int nq,
+                                                             int kprime) {
+    const int lane = threadIdx.x & 31;
+    const int q = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (q >= nq) return;
+    const unsigned raw = cnt[q];
+    const unsigned fl = flags[q];
+    if ((fl & 4u) && raw == (fl >> 8)) return;  // nothing appended since the last truncated state
+    if (raw > unsigned(SEL_WARP_MAX)) return;    // tc_select_kernel's share
+    uint64_t* base = cand + size_t(q) * TC_CAP;
+    const int n = int(raw);
+    uint64_t key[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        const int i = j * 32 + lane;
+        key[j] = (i < n) ? base[i] : 0ull;
+    }
+    int nv = 0;  // real candidates (unused reserved slots hold key 0)
+#pragma unroll
+    for (int j = 0; j < 32; ++j) nv += (key[j] != 0ull) ? 1 : 0;
+    nv = __reduce_add_sync(FULL, nv);
+    const bool select = nv >= kprime;  // otherwise every real candidate is kept and the threshold stays
+    uint32_t T = 0;                     // k'-th largest score word
+    if (select) {
+#pragma unroll 1
+        for (int bit = 31; bit >= 0; --bit) {
+            const uint32_t c = T | (1u << bit);
+            int ge = 0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) ge += (key[j] != 0ull && uint32_t(key[j] >> 32) >= c) ? 1 : 0;
+            if (__reduce_add_sync(FULL, ge) >= kprime) T = c;
+        }
+    }
+    // survivors: score word > T always; score word == T (ties at the threshold) until k' are kept
+    int above = 0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) above += (key[j] != 0ull && uint32_t(key[j] >> 32) > T) ? 1 : 0;
+    above = __reduce_add_sync(FULL, above);
+    int ties_left = select ? (kprime - above) : 0;
+    int out = 0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        const uint32_t hi = uint32_t(key[j] >> 32);
+        const bool real = key[j] != 0ull;
+        const bool is_tie = select && real && hi == T;
+        const unsigned tie_mask = __ballot_sync(FULL, is_tie);
+        const bool keep = real && (!select || hi > T || (is_tie && __popc(tie_mask & ((1u << lane) - 1u)) < ties_left));
+        const unsigned keep_mask = __ballot_sync(FULL, keep);
+        if (keep) base[out + __popc(keep_mask & ((1u << lane) - 1u))] = key[j];
+        out += __popc(keep_mask);
+        const int ties_taken = __popc(tie_mask);
+        ties_left -= (ties_taken < ties_left) ? ties_taken : ties_left;
+    }
+    if (lane == 0) {
+        cnt[q] = unsigned(out);
+        if (select) thr[q] = unorder_f32(T);  // k'-th best approximate score over the rows seen so far
+        flags[q] = (flags[q] & 0xFFu) | 4u | (unsigned(out) << 8);
+    }
+}
+
 __global__ void __launch_bounds__(256) tc_select_kernel(uint64_t* __restrict__ cand, unsigned* __restrict__ cnt,
                                                         float* __restrict__ thr, unsigned* __restrict__ flags,
                                                         unsigned* __restrict__ n_flagged, int kprime) {
@@ -436,7 +502,8 @@ __global__ void __launch_bounds__(256) tc_select_kernel(uint64_t* __restrict__ c
     const int q = blockIdx.x, tid = threadIdx.x;
     const unsigned raw = cnt[q];
     const unsigned fl = flags[q];
-    if ((fl & 4u) && raw == (fl >> 8)) return;  // nothing appended since the last (sorted, truncated) state
+    if ((fl & 4u) && raw == (fl >> 8)) return;  // nothing appended since the last truncated state
+    if (raw <= unsigned(SEL_WARP_MAX)) return;   // tc_select_warp_kernel's share
     if (raw > unsigned(TC_CAP)) {  // lost candidates: the query falls back to the exact scan
         if (tid == 0 && (atomicOr(flags + q, 1u) & 3u) == 0u) atomicAdd(n_flagged, 1u);
     }
@@ -488,6 +555,7 @@ struct TcRescoreParams {
     const uint64_t* cand;   // [nq][TC_CAP] sorted approximate keys
     const unsigned* cnt;    // [nq] <= kprime
     const float* q_norm;    // [nq] |q| as used
+    const float* thr;       // [nq] final approximate-score thresholds
     unsigned* flags;
     unsigned* n_flagged;
     int nq, k, kprime;
@@ -541,7 +609,7 @@ __global__ void __launch_bounds__(128) tc_rescore_kernel(const TcRescoreParams p
     // score) and therefore exact score <= t' + eps; the result is exact if the k-th exact score beats that.
     bool ok = true;
     if (n >= p.kprime) {
-        const float tprime = key_score(cand[p.kprime - 1]);
+        const float tprime = p.thr[q];  // k'-th best approximate score over all rows (last selection)
         const float sk = key_score(tk.thr);  // k-th best exact (thr == 0 -> -inf if fewer than k candidates)
         const float eps = p.eps_rel * p.q_norm[q] + 2e-5f;
         ok = sk > tprime + eps;
@@ -715,7 +783,7 @@ int tc_search(TcState* s, const float* q_dev, int nq, int k, int kprime, int qno
     const int nq_pad = n_qgroups * TC_QGROUP;
 
     // the first round (threshold -inf: every row is a candidate) covers at most CAP/2 rows and indexes by row
-    const int64_t first_tiles = (TC_CAP / 2) / TC_N;
+    const int64_t first_tiles = SEL_WARP_MAX / TC_N;
     const int64_t first_rows = (first_tiles * TC_N < s->n_rows) ? first_tiles * TC_N : s->n_rows;
     tc_prep_kernel<<<(nq_pad + 3) / 4, 128, 0, stream>>>(q_dev, nq, nq_pad, qnorm, s->qn, s->a_img, s->thr, s->cnt, s->flags,
                                                          s->q_norm, s->n_flagged, unsigned(first_rows));
@@ -749,9 +817,11 @@ int tc_search(TcState* s, const float* q_dev, int nq, int k, int kprime, int qno
         TC_CUDA(cudaGetLastError());
         if (timed) TC_CUDA(cudaEventRecord(s->ev[2 * rounds + 1], stream));
         ++rounds;
+        tc_select_warp_kernel<<<(nq + 3) / 4, 128, 0, stream>>>(s->cand, s->cnt, s->thr, s->flags, nq, kp);
+        TC_CUDA(cudaGetLastError());
         tc_select_kernel<<<nq, 256, TC_CAP * 8, stream>>>(s->cand, s->cnt, s->thr, s->flags, s->n_flagged, kp);
         TC_CUDA(cudaGetLastError());
-        *launches += 2;
+        *launches += 3;
         seen = t1;
         double g = double(TC_CAP - kp) / (2.0 * kp);
         if (g > s->growth) g = s->growth;
@@ -766,6 +836,7 @@ int tc_search(TcState* s, const float* q_dev, int nq, int k, int kprime, int qno
     rp.cand = s->cand;
     rp.cnt = s->cnt;
     rp.q_norm = s->q_norm;
+    rp.thr = s->thr;
     rp.flags = s->flags;
     rp.n_flagged = s->n_flagged;
     rp.nq = nq;
