@@ -119,6 +119,10 @@ int fcs_search_device(fcs_db* db, const float* q_dev, int nq, const int32_t* qle
 int fcs_merge_topk(int device, const uint64_t* keys_dev, int n_lists, int nq, int k, float* out_scores_dev,
                    int64_t* out_ids_dev, void* stream);
 
+/* last_search_ms needs fcs_set_profiling(db, 1) (two event records per call; off by default because an event
+ * between two scan kernels prevents their programmatic-dependent-launch overlap).  The TC path always times
+ * its GEMM launches (last_kernel_ms). */
+int fcs_set_profiling(fcs_db* db, int enable);
 int fcs_get_timing(const fcs_db* db, fcs_timing* out);
 
 /* Test hook (not part of the drop-in surface): the approximate bf16 tensor-core score of every

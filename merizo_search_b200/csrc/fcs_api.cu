@@ -66,6 +66,8 @@ struct fcs_db {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool ev_valid = false;
+    bool profiling = false;  // record ev0/ev1 around every search (off: event records between two scan kernels
+                             // would break their programmatic-dependent-launch overlap)
 
     uint64_t* gemv_scratch = nullptr;
     unsigned* ticket = nullptr;
@@ -402,7 +404,7 @@ static int search_core(fcs_db* db, const float* q_dev, int nq, const int32_t* ql
         return fail(FCS_ERR_UNSUPPORTED, "FCS_MODE_TC supports k <= %d (got %d)", tc_max_k(), k);
     int launches = 0;
     int fallbacks = 0;
-    FCS_CUDA(cudaEventRecord(db->ev0, stream));
+    if (db->profiling) FCS_CUDA(cudaEventRecord(db->ev0, stream));
     int rc = FCS_OK;
     if (use_mode == FCS_MODE_GEMV) {
         rc = gemv_search(db, q_dev, nq, qlen, mincov, k, qnorm, out_scores, out_ids, out_keys, stream, &launches);
@@ -418,8 +420,8 @@ static int search_core(fcs_db* db, const float* q_dev, int nq, const int32_t* ql
         }
     }
     if (rc != FCS_OK) return rc;
-    FCS_CUDA(cudaEventRecord(db->ev1, stream));
-    db->ev_valid = true;
+    if (db->profiling) FCS_CUDA(cudaEventRecord(db->ev1, stream));
+    db->ev_valid = db->profiling;
     db->timing.last_mode = use_mode;
     db->timing.last_launches = launches;
     db->timing.last_tc_fallbacks = fallbacks;
@@ -486,6 +488,13 @@ extern "C" int fcs_merge_topk(int device, const uint64_t* keys_dev, int n_lists,
     return FCS_OK;
 }
 
+extern "C" int fcs_set_profiling(fcs_db* db, int enable) {
+    if (!db) return fail(FCS_ERR_INVALID, "fcs_set_profiling: db is NULL");
+    db->profiling = enable != 0;
+    if (!db->profiling) db->ev_valid = false;
+    return FCS_OK;
+}
+
 extern "C" int fcs_get_timing(const fcs_db* db_c, fcs_timing* out) {
     if (!db_c || !out) return fail(FCS_ERR_INVALID, "fcs_get_timing: NULL argument");
     fcs_db* db = const_cast<fcs_db*>(db_c);
@@ -495,8 +504,15 @@ extern "C" int fcs_get_timing(const fcs_db* db_c, fcs_timing* out) {
         float ms = 0.f;
         FCS_CUDA(cudaEventElapsedTime(&ms, db->ev0, db->ev1));
         db->timing.last_search_ms = ms;
-        db->timing.last_kernel_ms = (db->timing.last_mode == FCS_MODE_TC && db->tc) ? tc_last_kernel_ms(db->tc) : ms;
-        db->timing.last_rounds = (db->timing.last_mode == FCS_MODE_TC && db->tc) ? tc_last_rounds(db->tc) : 1;
+        db->timing.last_kernel_ms = ms;
+    } else {
+        db->timing.last_search_ms = 0.f;
+        db->timing.last_kernel_ms = 0.f;
+    }
+    db->timing.last_rounds = 1;
+    if (db->timing.last_mode == FCS_MODE_TC && db->tc) {  // the TC path times its GEMM launches itself
+        db->timing.last_kernel_ms = tc_last_kernel_ms(db->tc);
+        db->timing.last_rounds = tc_last_rounds(db->tc);
     }
     *out = db->timing;
     return FCS_OK;

@@ -255,6 +255,11 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
         "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(cache_policy)
         : "memory");
 }
+// Programmatic dependent launch (PDL): a kernel launched with programmaticStreamSerialization may start while
+// its predecessor in the stream is still finishing; it must not touch anything the predecessor writes before
+// pdl_wait(), and the predecessor lets dependents start early with pdl_launch_dependents().
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 // named barriers (id 1..15): arrive does not block, sync does
 __device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
     asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");

@@ -106,6 +106,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemv_topk_kernel(const GemvParams
         __syncwarp();
     } else {
         // ------------------------------------------------------------------ consumers
+        // Everything a predecessor kernel on the stream may have written (the queries, the previous pass's keys,
+        // and -- at the end -- scratch/ticket/outputs) is touched only after this point; the producer warp is
+        // already prefetching database rows (immutable after finalize) into the ring meanwhile.
+        pdl_wait();
         // query normalisation fused here (dbsearch.py:78 cosine eps 1e-8 / dbsearch.py:304 F.normalize eps 1e-12)
         if (warp < NQ) {
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -179,7 +183,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemv_topk_kernel(const GemvParams
     }
 
     // ---------------------------------------------------------------------- CTA-level merge
+    if (warp == NWARPS) pdl_wait();  // the producer warp joins the writes below (consumers waited above)
     __syncthreads();  // every bulk copy has landed and been consumed: the ring can be reused
+    pdl_launch_dependents();  // the next search on this stream may start prefetching while we merge
     uint64_t* lists = reinterpret_cast<uint64_t*>(ring);  // [NQ][NWARPS][k]
     if (warp < NWARPS) {
 #pragma unroll
@@ -256,8 +262,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemv_topk_kernel(const GemvParams
 
 template <int NQ, int KPL>
 cudaError_t launch_inst(const GemvParams& p, int grid, cudaStream_t stream) {
-    gemv_topk_kernel<NQ, KPL><<<grid, NTHREADS, SMEM_BYTES, stream>>>(p);
-    return cudaGetLastError();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(NTHREADS);
+    cfg.dynamicSmemBytes = SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, gemv_topk_kernel<NQ, KPL>, p);
 }
 
 template <int NQ, int KPL>

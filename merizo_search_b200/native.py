@@ -25,7 +25,7 @@ MODE_AUTO, MODE_GEMV, MODE_TC = 0, 1, 2
 EXPORTS = [
     "fcs_version", "fcs_last_error", "fcs_device_count", "fcs_db_create", "fcs_db_upload",
     "fcs_db_upload_device", "fcs_db_finalize", "fcs_db_get_info", "fcs_db_destroy", "fcs_search",
-    "fcs_search_device", "fcs_merge_topk", "fcs_get_timing", "fcs_debug_tc_approx",
+    "fcs_search_device", "fcs_merge_topk", "fcs_get_timing", "fcs_set_profiling", "fcs_debug_tc_approx",
 ]
 
 
@@ -82,6 +82,7 @@ def load() -> C.CDLL:
     lib.fcs_merge_topk.argtypes = [i32, vp, i32, i32, i32, vp, vp, vp]
     lib.fcs_get_timing.argtypes = [vp, C.POINTER(Timing)]
     lib.fcs_debug_tc_approx.argtypes = [vp, vp, i32, i32, vp]
+    lib.fcs_set_profiling.argtypes = [vp, i32]
     for name in EXPORTS:
         if name not in ("fcs_last_error",):
             getattr(lib, name).restype = C.c_int
@@ -166,6 +167,9 @@ class Database:
         out = np.empty((q.shape[0], self.n_rows), dtype=np.float32)
         _check(self._lib.fcs_debug_tc_approx(self._h, _np_ptr(q), q.shape[0], int(qnorm), _np_ptr(out)))
         return out
+
+    def set_profiling(self, enable: bool) -> None:
+        _check(self._lib.fcs_set_profiling(self._h, 1 if enable else 0))
 
     def timing(self) -> Timing:
         t = Timing()
