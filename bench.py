@@ -63,7 +63,7 @@ class ClockSampler:
         q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(gpu_index)], stdout=self.tmp, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -72,7 +72,7 @@ class ClockSampler:
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         if self.proc is None:
             return out
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
@@ -262,20 +262,22 @@ def run_gpu(args, wl, wl_name):
     value = nq / (ms_per_step * 1e-3)
     timing = h.timing()
 
-    # ---- e2e: host buffers through the public host API (H2D + D2H inside the timed region)
+    # ---- e2e: host buffers through the public API (H2D + D2H inside the timed region).
+    # 1 GPU: native.Database.search (fcs_search).  N GPUs: engine.DistributedEngine.search_host (pinned host
+    # queries -> H2D -> shard search -> NCCL all-gather of keys -> GPU merge -> D2H) on every rank.
+    deng = None
+    if world > 1:
+        from merizo_search_b200.engine import DistributedEngine
+
+        deng = DistributedEngine(rows_total, rank=rank, world_size=world, device=local_rank, create_handle=False)
+        deng.db = h
+
     def step_e2e():
-        s_h, i_h = h.search(q_host.numpy(), k, qlen=qlen, mincov=mincov, mode=mode)
-        if world > 1:
-            from merizo_search_b200.engine import encode_keys
-            kh = torch.from_numpy(encode_keys(s_h, i_h).view(np.int64)).pin_memory()
-            with torch.cuda.stream(stream):
-                keys.copy_(kh, non_blocking=True)
-                dist.all_gather_into_tensor(gathered.view(world * nq, k), keys)
-                native.merge_topk(local_rank, gathered.data_ptr(), world, nq, k, sc.data_ptr(), ids.data_ptr(),
-                                  stream=stream.cuda_stream)
-                s_h = sc.cpu()
-                i_h = ids.cpu()
-        return s_h, i_h
+        if world == 1:
+            return h.search(q_host.numpy(), k, qlen=qlen, mincov=mincov, mode=mode)
+        with torch.cuda.stream(stream):
+            out_ = deng.search_host(q_host, k, qlen=qlen, mincov=mincov, mode=mode)
+        return out_
 
     for _ in range(max(1, args.warmup // 2)):
         step_e2e()
@@ -322,7 +324,9 @@ def run_gpu(args, wl, wl_name):
                        "db_load_s": round(t_load, 2), "tc_fallback_queries": int(timing.last_tc_fallbacks)},
             "e2e": {"value": nq / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": int(nq * 512),
                     "d2h_bytes_per_step": int(nq * k * 12), "ms_per_step": e2e_s * 1e3,
-                    "api": "merizo_search_b200.native.Database.search (fcs_search: pinned host queries in, host scores/ids out)"},
+                    "api": ("merizo_search_b200.native.Database.search (fcs_search: pinned host queries in, host scores/ids out)"
+                            if world == 1 else "merizo_search_b200.engine.DistributedEngine.search_host (H2D, shard search, "
+                            "NCCL all-gather of keys, GPU merge, D2H on every rank)")},
             "gpu_launches": int(launches),
             "roofline": roof,
             "clocks": clocks,
@@ -345,8 +349,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
-    if args.steps <= 0:
-        args.steps = 20 if wl["mode"] == "tc" else 200
+    if args.steps <= 0:  # long enough (>= ~0.2 s) for nvidia-smi to sample clocks inside the timed region
+        args.steps = {"cfg3": 20, "cfg2": 4000, "cfg4": 60}[args.workload]
     if args.warmup <= 0:
         args.warmup = 3 if wl["mode"] == "tc" else 10
     args.warmup = max(args.warmup, 3)

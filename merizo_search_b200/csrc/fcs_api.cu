@@ -84,6 +84,7 @@ struct fcs_db {
     size_t h_q_cap = 0;
     float* h_scores = nullptr;
     int64_t* h_ids = nullptr;
+    uint64_t* h_keys = nullptr;  // only for the zero-copy small-result path
     size_t h_out_cap = 0;
 
     void* h_stage[2] = {nullptr, nullptr};
@@ -127,10 +128,12 @@ static int ensure_out_bufs(fcs_db* db, size_t entries, bool host) {
     if (host && db->h_out_cap < entries) {
         if (db->h_scores) cudaFreeHost(db->h_scores);
         if (db->h_ids) cudaFreeHost(db->h_ids);
-        db->h_scores = nullptr; db->h_ids = nullptr;
+        if (db->h_keys) cudaFreeHost(db->h_keys);
+        db->h_scores = nullptr; db->h_ids = nullptr; db->h_keys = nullptr;
         db->h_out_cap = 0;
         FCS_CUDA(cudaMallocHost(&db->h_scores, entries * sizeof(float)));
         FCS_CUDA(cudaMallocHost(&db->h_ids, entries * sizeof(int64_t)));
+        FCS_CUDA(cudaMallocHost(&db->h_keys, entries * sizeof(uint64_t)));
         db->h_out_cap = entries;
     }
     return FCS_OK;
@@ -225,6 +228,7 @@ extern "C" int fcs_db_destroy(fcs_db* db) {
     if (db->h_q) cudaFreeHost(db->h_q);
     if (db->h_scores) cudaFreeHost(db->h_scores);
     if (db->h_ids) cudaFreeHost(db->h_ids);
+    if (db->h_keys) cudaFreeHost(db->h_keys);
     for (int i = 0; i < 2; ++i) {
         if (db->h_stage[i]) cudaFreeHost(db->h_stage[i]);
         if (db->stage_ev[i]) cudaEventDestroy(db->stage_ev[i]);
@@ -454,12 +458,23 @@ extern "C" int fcs_search(fcs_db* db, const float* q, int nq, const int32_t* qle
     if ((rc = ensure_query_bufs(db, size_t(nq), true)) != FCS_OK) return rc;
     if ((rc = ensure_out_bufs(db, entries, true)) != FCS_OK) return rc;
     memcpy(db->h_q, q, size_t(nq) * DIM * sizeof(float));
-    FCS_CUDA(cudaMemcpyAsync(db->d_q, db->h_q, size_t(nq) * DIM * sizeof(float), cudaMemcpyHostToDevice, db->stream));
-    rc = search_core(db, db->d_q, nq, qlen, mincov, k, qnorm, mode, kprime, db->d_scores, db->d_ids, db->d_keys, db->stream);
-    if (rc != FCS_OK) return rc;
-    FCS_CUDA(cudaMemcpyAsync(db->h_scores, db->d_scores, entries * sizeof(float), cudaMemcpyDeviceToHost, db->stream));
-    FCS_CUDA(cudaMemcpyAsync(db->h_ids, db->d_ids, entries * sizeof(int64_t), cudaMemcpyDeviceToHost, db->stream));
-    FCS_CUDA(cudaStreamSynchronize(db->stream));
+    // Small exact-scan searches (the per-query loop of the reference's torch flavour) run zero-copy: the kernel
+    // reads the queries from, and writes the k results to, pinned host memory (UVA), so the call is one launch
+    // plus one stream synchronisation instead of launch + three copies.
+    const bool gemv = mode == FCS_MODE_GEMV || (mode == FCS_MODE_AUTO && !(db->tc && nq >= tc_min_batch() && k <= tc_max_k() &&
+                                                                          !(qlen != nullptr && db->lens != nullptr)));
+    if (gemv && k <= GEMV_MAX_K && nq <= 64) {
+        rc = search_core(db, db->h_q, nq, qlen, mincov, k, qnorm, FCS_MODE_GEMV, kprime, db->h_scores, db->h_ids, db->h_keys, db->stream);
+        if (rc != FCS_OK) return rc;
+        FCS_CUDA(cudaStreamSynchronize(db->stream));
+    } else {
+        FCS_CUDA(cudaMemcpyAsync(db->d_q, db->h_q, size_t(nq) * DIM * sizeof(float), cudaMemcpyHostToDevice, db->stream));
+        rc = search_core(db, db->d_q, nq, qlen, mincov, k, qnorm, mode, kprime, db->d_scores, db->d_ids, db->d_keys, db->stream);
+        if (rc != FCS_OK) return rc;
+        FCS_CUDA(cudaMemcpyAsync(db->h_scores, db->d_scores, entries * sizeof(float), cudaMemcpyDeviceToHost, db->stream));
+        FCS_CUDA(cudaMemcpyAsync(db->h_ids, db->d_ids, entries * sizeof(int64_t), cudaMemcpyDeviceToHost, db->stream));
+        FCS_CUDA(cudaStreamSynchronize(db->stream));
+    }
     memcpy(out_scores, db->h_scores, entries * sizeof(float));
     memcpy(out_ids, db->h_ids, entries * sizeof(int64_t));
     return FCS_OK;

@@ -183,6 +183,19 @@ class DistributedEngine:
         self.db.search_device(q_dev.data_ptr(), nq, k, 0, 0, out_keys_ptr=keys.data_ptr(), stream=st.cuda_stream, **kw)
         return keys
 
+    def search_host(self, q_host, k: int, **kw):
+        """Host arrays in (the same queries on every rank), host arrays out: H2D copy, shard search, NCCL key
+        all-gather, GPU merge, D2H copy.  This is the end-to-end call of the one-rank-per-GPU deployment."""
+        import torch
+
+        dev = torch.device("cuda", self.device or 0)
+        qh = torch.as_tensor(q_host, dtype=torch.float32).reshape(-1, DIM)
+        if not qh.is_pinned():
+            qh = qh.pin_memory()
+        q_dev = qh.to(dev, non_blocking=True)
+        sc, ids = self.search(q_dev, k, **kw)
+        return sc.cpu().numpy(), ids.cpu().numpy()
+
     def search(self, q_dev, k: int, local_search=None, merge=None, **kw):
         """Replicated queries in, identical (scores, ids) on every rank out (torch tensors)."""
         import torch

@@ -61,9 +61,8 @@ def load() -> C.CDLL:
     if not os.path.exists(path) or (not _build.is_fresh() and os.environ.get("FCS_NO_REBUILD") != "1"):
         try:
             _build.build()
-        except Exception as exc:  # no silent fallback: the product needs the CUDA library
-            if not os.path.exists(path):
-                raise FcsError(ERR_STATE, f"libfcsearch.so is missing and could not be built: {exc}") from exc
+        except Exception as exc:  # no silent fallback, and never a stale binary: the product needs THIS source built
+            raise FcsError(ERR_STATE, f"libfcsearch.so is missing or stale and could not be (re)built: {exc}") from exc
     lib = C.CDLL(path)
     vp, i64, i32, u32, f32 = C.c_void_p, C.c_int64, C.c_int, C.c_uint32, C.c_float
     lib.fcs_version.restype = C.c_int
