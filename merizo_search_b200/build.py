@@ -41,7 +41,7 @@ def _source_hash() -> str:
     files = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))] + [os.path.join(INCLUDE, "fcsearch.h")]
     for f in files:
         with open(f, "rb") as fh:
-            h.update(f.encode())
+            h.update(os.path.basename(f).encode())  # not the absolute path: the tree is copied to other machines
             h.update(fh.read())
     h.update(" ".join(NVCC_FLAGS).encode())
     return h.hexdigest()
@@ -58,6 +58,21 @@ def build(force: bool = False, verbose: bool = False) -> str:
     """Compile every .cu under csrc/ for sm_100a and link libfcsearch.so.  Returns its path."""
     if not force and is_fresh():
         return LIB_PATH
+    # several ranks of one job may get here at the same time: one builds, the others wait and re-check
+    import fcntl
+
+    lock = open(os.path.join(PKG_DIR, ".build.lock"), "w")
+    fcntl.flock(lock, fcntl.LOCK_EX)
+    try:
+        if not force and is_fresh():
+            return LIB_PATH
+        return _build_locked(verbose)
+    finally:
+        fcntl.flock(lock, fcntl.LOCK_UN)
+        lock.close()
+
+
+def _build_locked(verbose: bool) -> str:
     nvcc = _nvcc()
     objs = []
     build_dir = os.path.join(PKG_DIR, "build")

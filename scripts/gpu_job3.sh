@@ -1,0 +1,2 @@
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_fullsize_gpu.py -x -q 2>&1 | tail -12
