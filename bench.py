@@ -180,8 +180,20 @@ def run_gpu(args, wl, wl_name):
     rows_total = wl["rows"] * (world if wl["scaling"] == "weak" else 1)
     if args.rows:
         rows_total = args.rows
-    r0, r1 = shard_ranges(rows_total, world)[rank]
+    # N>1 layout: world = R row shards x Q query groups (engine.DistributedEngine); Q=1 is pure row sharding
+    from merizo_search_b200.engine import DistributedEngine
+
+    qg = args.query_groups
+    if world == 1:
+        qg = 1
+    elif qg <= 0:
+        qg = DistributedEngine.auto_query_groups(rows_total, world, bytes_per_row=514 + (256 if wl["mode"] == "tc" else 0))
+    while qg > 1 and (world % qg != 0 or qg > nq):
+        qg -= 1
+    n_shards = world // qg
+    r0, r1 = shard_ranges(rows_total, n_shards)[rank // qg]
     n_local = r1 - r0
+    nq_local = -(-nq // qg)
     mode = native.MODE_TC if wl["mode"] == "tc" else native.MODE_GEMV
 
     # ---- database: generated on the device block by block, uploaded into the handle, finalized
@@ -211,20 +223,23 @@ def run_gpu(args, wl, wl_name):
     keys = torch.empty((nq, k), dtype=torch.int64, device=dev)
     sc = torch.empty((nq, k), dtype=torch.float32, device=dev)
     ids = torch.empty((nq, k), dtype=torch.int64, device=dev)
-    gathered = torch.empty((world, nq, k), dtype=torch.int64, device=dev) if world > 1 else None
     launches = 0
+    deng = None
+    if world > 1:
+        deng = DistributedEngine(rows_total, rank=rank, world_size=world, device=local_rank, create_handle=False, query_groups=qg)
+        deng.db = h
+        assert (deng.row0, deng.row1) == (r0, r1)
 
     def step_device():
         nonlocal launches
         with torch.cuda.stream(stream):
-            h.search_device(q_dev.data_ptr(), nq, k, sc.data_ptr(), ids.data_ptr(), out_keys_ptr=keys.data_ptr(),
-                            qlen=qlen, mincov=mincov, mode=mode, stream=stream.cuda_stream)
-            launches += launches_per_search
-            if world > 1:
-                dist.all_gather_into_tensor(gathered.view(world * nq, k), keys)
-                native.merge_topk(local_rank, gathered.data_ptr(), world, nq, k, sc.data_ptr(), ids.data_ptr(),
-                                  stream=stream.cuda_stream)
-                launches += 1
+            if world == 1:
+                h.search_device(q_dev.data_ptr(), nq, k, sc.data_ptr(), ids.data_ptr(), out_keys_ptr=keys.data_ptr(),
+                                qlen=qlen, mincov=mincov, mode=mode, stream=stream.cuda_stream)
+                launches += launches_per_search
+            else:  # shard search -> ONE NCCL all-gather of packed keys -> merge kernel, on every rank
+                deng.search(q_dev, k, qlen=qlen, mincov=mincov, mode=mode)
+                launches += launches_per_search + 1
 
     def barrier():
         torch.cuda.synchronize()
@@ -265,13 +280,6 @@ def run_gpu(args, wl, wl_name):
     # ---- e2e: host buffers through the public API (H2D + D2H inside the timed region).
     # 1 GPU: native.Database.search (fcs_search).  N GPUs: engine.DistributedEngine.search_host (pinned host
     # queries -> H2D -> shard search -> NCCL all-gather of keys -> GPU merge -> D2H) on every rank.
-    deng = None
-    if world > 1:
-        from merizo_search_b200.engine import DistributedEngine
-
-        deng = DistributedEngine(rows_total, rank=rank, world_size=world, device=local_rank, create_handle=False)
-        deng.db = h
-
     def step_e2e():
         if world == 1:
             return h.search(q_host.numpy(), k, qlen=qlen, mincov=mincov, mode=mode)
@@ -296,7 +304,7 @@ def run_gpu(args, wl, wl_name):
     if rank == 0:
         kms = float(np.mean(kernel_ms))
         if wl["mode"] == "tc":
-            flops = 2.0 * nq * n_local * 128
+            flops = 2.0 * nq_local * n_local * 128  # this GPU's share: its query slice against its row shard
             achieved = flops / (kms * 1e-3) / 1e12
             roof = dict(bound="tensor", achieved=achieved, peak=peaks["tensor"], unit="TFLOP/s", frac=achieved / peaks["tensor"],
                         traffic=None, kernel="tc_gemm_filter_kernel (all rounds of one search)",
@@ -320,7 +328,9 @@ def run_gpu(args, wl, wl_name):
             "config": {"workload": wl_name, "description": wl["desc"], "rows_total": rows_total, "rows_per_gpu": n_local,
                        "nq": nq, "k": k, "path": wl["mode"], "coverage_mask": wl["mask"],
                        "l2": "inputs larger than L2 (database streamed from HBM every step)",
-                       "parallelism": f"row-sharded x{world}, NCCL all-gather of packed keys + GPU merge" if world > 1 else "single GPU",
+                       "parallelism": (f"{n_shards} row shard(s) x {qg} query group(s) over {world} ranks, one NCCL all-gather of "
+                                       "packed keys + GPU merge") if world > 1 else "single GPU",
+                       "queries_per_gpu": nq_local,
                        "db_load_s": round(t_load, 2), "tc_fallback_queries": int(timing.last_tc_fallbacks)},
             "e2e": {"value": nq / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": int(nq * 512),
                     "d2h_bytes_per_step": int(nq * k * 12), "ms_per_step": e2e_s * 1e3,
@@ -347,6 +357,9 @@ def main():
     ap.add_argument("--workload", default=os.environ.get("FCS_BENCH_WORKLOAD", DEFAULT_WORKLOAD), choices=sorted(WORKLOADS))
     ap.add_argument("--rows", type=int, default=0, help="override the total row count (debugging)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--query-groups", type=int, default=0,
+                    help="N>1: ranks = row shards x query groups; 0 = auto (replicate the database as far as ~80 GB per "
+                         "GPU allow and split the batch), 1 = pure row sharding")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.steps <= 0:  # long enough (>= ~0.2 s) for nvidia-smi to sample clocks inside the timed region

@@ -154,33 +154,68 @@ class LocalEngine:
 
 
 class DistributedEngine:
-    """One rank per GPU (torchrun).  ``local_search`` and ``merge`` are injectable so that the rank
+    """One rank per GPU (torchrun).  The world is laid out as R row shards x Q query groups (world = R*Q,
+    rank = r*Q + j): rank (r, j) holds row shard r and searches query slice j, so a database that fits in fewer
+    than `world` shards is replicated Q times and large batches are split instead of being repeated on every GPU.
+    Q = 1 is pure row sharding (the only option at TED scale).  One all-gather of the packed keys, then the R
+    lists of every query are merged on every rank.  ``local_search`` and ``merge`` are injectable so that the rank
     plumbing (partition, offsets, all-gather layout) is testable on CPU with the gloo backend."""
 
     def __init__(self, n_rows_global: int, rank: Optional[int] = None, world_size: Optional[int] = None,
                  device: Optional[int] = None, normalise_rows: bool = False, keep_bf16: bool = False,
-                 has_lengths: bool = False, create_handle: bool = True):
+                 has_lengths: bool = False, create_handle: bool = True, query_groups: int = 1):
         import torch.distributed as dist
 
         self.rank = dist.get_rank() if rank is None else rank
         self.world = dist.get_world_size() if world_size is None else world_size
+        if query_groups < 1 or self.world % query_groups != 0:
+            raise ValueError(f"query_groups={query_groups} must divide the world size {self.world}")
+        self.q_groups = int(query_groups)
+        self.row_shards = self.world // self.q_groups
+        self.shard_index, self.q_index = divmod(self.rank, self.q_groups)
         self.n_rows_global = int(n_rows_global)
-        self.ranges = shard_ranges(self.n_rows_global, self.world)
-        self.row0, self.row1 = self.ranges[self.rank]
+        self.ranges = shard_ranges(self.n_rows_global, self.row_shards)
+        self.row0, self.row1 = self.ranges[self.shard_index]
         self.device = device
+        self._side = None
         self.db: Optional[native.Database] = None
         if create_handle:
             self.db = native.Database(self.row1 - self.row0, device=device or 0, id_offset=self.row0,
                                       normalise_rows=normalise_rows, keep_bf16=keep_bf16, has_lengths=has_lengths)
 
-    def local_keys(self, q_dev, nq: int, k: int, **kw):
+    @staticmethod
+    def auto_query_groups(n_rows_global: int, world: int, bytes_per_row: int = 512 + 256, budget_bytes: float = 80e9) -> int:
+        """Largest Q dividing `world` such that a row shard of N/(world/Q) rows fits `budget_bytes` per GPU."""
+        best = 1
+        for q in range(1, world + 1):
+            if world % q == 0 and -(-n_rows_global // (world // q)) * bytes_per_row <= budget_bytes:
+                best = q
+        return best
+
+    def query_slice(self, nq: int) -> Tuple[int, int, int]:
+        """(first query, one-past-last, padded slice length) of this rank's query group."""
+        per = -(-nq // self.q_groups)
+        lo = min(nq, self.q_index * per)
+        return lo, min(nq, lo + per), per
+
+    def local_keys(self, q_dev, nq: int, k: int, qlen=None, **kw):
         """This rank's [nq,k] packed keys (torch int64 CUDA tensor viewing uint64 keys)."""
         import torch
 
         dev = torch.device("cuda", self.device or 0)
-        keys = torch.empty((nq, k), dtype=torch.int64, device=dev)
-        st = torch.cuda.current_stream(dev)
-        self.db.search_device(q_dev.data_ptr(), nq, k, 0, 0, out_keys_ptr=keys.data_ptr(), stream=st.cuda_stream, **kw)
+        keys = torch.zeros((nq, k), dtype=torch.int64, device=dev)
+        cur = torch.cuda.current_stream(dev)
+        if cur.cuda_stream != 0:
+            self.db.search_device(q_dev.data_ptr(), nq, k, 0, 0, out_keys_ptr=keys.data_ptr(), stream=cur.cuda_stream, qlen=qlen, **kw)
+        else:
+            # the library reads stream 0 as "the handle's own stream": never launch on the legacy default stream,
+            # use a side stream ordered after what produced the queries and before what consumes the keys
+            if self._side is None:
+                self._side = torch.cuda.Stream(dev)
+            self._side.wait_stream(cur)
+            self.db.search_device(q_dev.data_ptr(), nq, k, 0, 0, out_keys_ptr=keys.data_ptr(), stream=self._side.cuda_stream,
+                                  qlen=qlen, **kw)
+            cur.wait_stream(self._side)
         return keys
 
     def search_host(self, q_host, k: int, **kw):
@@ -196,21 +231,36 @@ class DistributedEngine:
         sc, ids = self.search(q_dev, k, **kw)
         return sc.cpu().numpy(), ids.cpu().numpy()
 
-    def search(self, q_dev, k: int, local_search=None, merge=None, **kw):
+    def search(self, q_dev, k: int, local_search=None, merge=None, qlen=None, **kw):
         """Replicated queries in, identical (scores, ids) on every rank out (torch tensors)."""
         import torch
         import torch.distributed as dist
 
         nq = q_dev.shape[0]
-        keys = local_search(q_dev, nq, k) if local_search else self.local_keys(q_dev, nq, k, **kw)
-        gathered = torch.empty((self.world, nq, k), dtype=keys.dtype, device=keys.device)
-        # the one collective on the path: 8 B per entry (flat [world*nq, k] view: the layout gloo and nccl both accept)
-        dist.all_gather_into_tensor(gathered.view(self.world * nq, k), keys)
+        lo, hi, per = self.query_slice(nq)
+        q_mine = q_dev[lo:hi]
+        ql_mine = None if qlen is None else np.asarray(qlen)[lo:hi]
+        if hi - lo > 0:
+            if local_search:
+                keys = local_search(q_mine, hi - lo, k)
+            else:
+                keys = self.local_keys(q_mine, hi - lo, k, qlen=ql_mine, **kw)
+        else:
+            keys = torch.zeros((0, k), dtype=torch.int64, device=q_dev.device)
+        if hi - lo < per:  # pad the slice: every rank contributes the same shape; key 0 = empty
+            pad = torch.zeros((per - (hi - lo), k), dtype=torch.int64, device=keys.device)
+            keys = torch.cat([keys, pad], dim=0)
+        gathered = torch.empty((self.world, per, k), dtype=keys.dtype, device=keys.device)
+        # the one collective on the path: 8 B per entry (flat [world*per, k] view: the layout gloo and nccl both accept)
+        dist.all_gather_into_tensor(gathered.view(self.world * per, k), keys.contiguous())
+        # rank = r*Q + j  =>  gathered is [R][Q*per][k]: R sorted lists for each of the Q*per (padded) queries
+        lists = gathered.view(self.row_shards, self.q_groups * per, k)
         if merge:
-            return merge(gathered, k)
-        sc = torch.empty((nq, k), dtype=torch.float32, device=keys.device)
-        ids = torch.empty((nq, k), dtype=torch.int64, device=keys.device)
-        st = torch.cuda.current_stream(keys.device)
-        native.merge_topk(self.device or 0, gathered.data_ptr(), self.world, nq, k, sc.data_ptr(), ids.data_ptr(),
-                          stream=st.cuda_stream)
-        return sc, ids
+            sc, ids = merge(lists, k)
+        else:
+            sc = torch.empty((self.q_groups * per, k), dtype=torch.float32, device=keys.device)
+            ids = torch.empty((self.q_groups * per, k), dtype=torch.int64, device=keys.device)
+            st = torch.cuda.current_stream(keys.device)
+            native.merge_topk(self.device or 0, lists.data_ptr(), self.row_shards, self.q_groups * per, k, sc.data_ptr(),
+                              ids.data_ptr(), stream=st.cuda_stream)
+        return sc[:nq], ids[:nq]

@@ -1,3 +1,2 @@
 mkdir -p gpurun_out
-timeout 120 python bench.py --workload cfg3 --rows 1250000 --steps 5 --warmup 3 --no-cpu-baseline 2>&1 | tail -4 | cut -c1-600
-echo "exit: $?"
+timeout 300 python -m pytest tests/test_gemv_gpu.py -x -q -k "back_to_back" 2>&1 | tail -15

@@ -19,15 +19,17 @@ def main():
     n, nq, k = 90001, 130, 10
     db = synth.host_db(n, base_seed=91)  # every rank regenerates the same synthetic matrix and keeps its slice
     q = torch.from_numpy(synth.host_queries(nq, 91, normalise=True)).to(dev)
-    eng = engine.DistributedEngine(n, device=local, keep_bf16=True)
-    eng.db.upload(0, db[eng.row0:eng.row1])
-    eng.db.finalize()
     res = {}
-    for tag, mode in (("gemv", native.MODE_GEMV), ("tc", native.MODE_TC)):
-        s, i = eng.search(q, k, mode=mode)
-        torch.cuda.synchronize()
-        res[f"s_{tag}"] = s.cpu().numpy()
-        res[f"i_{tag}"] = i.cpu().numpy()
+    for qg in (1, dist.get_world_size()):  # pure row sharding, then full replication with the queries split
+        eng = engine.DistributedEngine(n, device=local, keep_bf16=True, query_groups=qg)
+        eng.db.upload(0, db[eng.row0:eng.row1])
+        eng.db.finalize()
+        for tag, mode in (("gemv", native.MODE_GEMV), ("tc", native.MODE_TC)):
+            s, i = eng.search(q, k, mode=mode)
+            torch.cuda.synchronize()
+            res[f"s_{tag}{qg}"] = s.cpu().numpy()
+            res[f"i_{tag}{qg}"] = i.cpu().numpy()
+        eng.db.close()
     gathered = [None] * dist.get_world_size()
     dist.all_gather_object(gathered, {k_: v.tobytes() for k_, v in res.items()})
     assert all(g == gathered[0] for g in gathered), "ranks disagree on the merged result"

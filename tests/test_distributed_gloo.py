@@ -12,7 +12,7 @@ import torch.multiprocessing as mp
 from merizo_search_b200 import engine, synth
 from oracle import foldclass_oracle as orc
 
-N, NQ, K = 5001, 6, 9
+N, NQ, K = 5001, 7, 9
 
 
 def _free_port():
@@ -21,15 +21,15 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, out_dir):
+def _worker(rank, world, port, out_dir, q_groups):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         db = synth.host_db(N, base_seed=12)
         q = torch.from_numpy(synth.host_queries(NQ, 12, normalise=True))
-        eng = engine.DistributedEngine(N, create_handle=False)
+        eng = engine.DistributedEngine(N, create_handle=False, query_groups=q_groups)
         lo, hi = eng.row0, eng.row1
-        assert (lo, hi) == engine.shard_ranges(N, world)[rank]
+        assert (lo, hi) == engine.shard_ranges(N, world // q_groups)[rank // q_groups]
 
         def local_search(qt, nq, k):  # oracle on this rank's rows, global ids = local + offset
             D, I = orc.knn_exact_blockwise(qt.numpy(), orc.db_iterator(db[lo:hi], 1024), k)
@@ -46,9 +46,10 @@ def _worker(rank, world, port, out_dir):
 
 
 @pytest.mark.timeout(300)
-def test_two_rank_search_equals_single_shard_oracle(tmp_path):
+@pytest.mark.parametrize("q_groups", [1, 2])  # 2 row shards x 1 query group, and 1 shard replicated x 2 query groups
+def test_two_rank_search_equals_single_shard_oracle(tmp_path, q_groups):
     world, port = 2, _free_port()
-    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, str(tmp_path), q_groups), nprocs=world, join=True)
     db = synth.host_db(N, base_seed=12)
     q = synth.host_queries(NQ, 12, normalise=True)
     D, I = orc.knn_exact_blockwise(q, orc.db_iterator(db, 262144), K)

@@ -81,6 +81,24 @@ def test_ragged_sizes_and_k(n, k):
     h.close()
 
 
+def test_many_query_groups_back_to_back():
+    """nq > 8 = several launches in a row on one stream (they overlap through programmatic dependent launch and
+    share the handle's scratch): every group must still be exact."""
+    n, nq, k = 60000, 130, 10
+    db = synth.host_db(n, base_seed=15)
+    q = synth.host_queries(nq, 15, normalise=True)
+    h = native.Database(n)
+    h.upload(0, db)
+    h.finalize()
+    D, I = orc.knn_exact_blockwise(q, orc.db_iterator(db, 262144), k)
+    full = orc.all_scores_ip(q, db)
+    for rep in range(3):
+        s, i = h.search(q, k, mode=native.MODE_GEMV)
+        for r in range(nq):
+            orc.check_topk(s[r], i[r], D[r], I[r], full[r], tol=TOL)
+    h.close()
+
+
 def test_all_rows_masked_gives_zero_scores():
     n = 2000
     db = synth.host_db(n, base_seed=5, normalise=False)

@@ -49,6 +49,6 @@ def test_torchrun_two_ranks_nccl_allgather_merge(tmp_path):
     q = synth.host_queries(nq, 91, normalise=True)
     D, I = orc.knn_exact_blockwise(q, orc.db_iterator(db, 262144), k)
     full = orc.all_scores_ip(q, db)
-    for tag in ("gemv", "tc"):
+    for tag in ("gemv1", "tc1", "gemv2", "tc2"):  # row-sharded (1 query group) and replicated (2 query groups)
         for r_ in range(nq):
             orc.check_topk(z[f"s_{tag}"][r_], z[f"i_{tag}"][r_], D[r_], I[r_], full[r_], tol=1e-5)
