@@ -396,12 +396,25 @@ static int gemv_search(fcs_db* db, const float* q, int nq, const int32_t* qlen, 
     return FCS_OK;
 }
 
+// AUTO: the batched tensor-core path pays a fixed ~0.4 ms (threshold warm-up rounds, selection launches) and then
+// ~256 flop per (query,row) at ~1.1 PFLOP/s; the exact scan streams 512 B per row once per 8 queries at ~6.5 TB/s
+// with ~10 us per launch.  Pick the cheaper estimate.
+static bool auto_prefers_tc(const fcs_db* db, int nq, int k, bool mask_on) {
+    if (!db->tc || mask_on || k > tc_max_k() || nq < tc_min_batch()) return false;
+    const double rows = double(db->n_rows);
+    const double groups = double((nq + GEMV_MAX_NQ - 1) / GEMV_MAX_NQ);
+    const double t_gemv = groups * (1.0e-5 + rows * 512.0 / 6.5e12 * 1.35);
+    const double nq_pad = double((nq + 511) / 512 * 512);
+    const double t_tc = 4.0e-4 + rows * 256.0 / 5.0e12 + nq_pad * rows * 256.0 / 1.1e15;
+    return t_tc < t_gemv;
+}
+
 static int search_core(fcs_db* db, const float* q_dev, int nq, const int32_t* qlen, float mincov, int k,
                        int qnorm, int mode, int kprime, float* out_scores, int64_t* out_ids, uint64_t* out_keys,
                        cudaStream_t stream) {
     int use_mode = mode;
     const bool mask_on = qlen != nullptr && db->lens != nullptr;
-    if (use_mode == FCS_MODE_AUTO) use_mode = (db->tc && !mask_on && nq >= tc_min_batch() && k <= tc_max_k()) ? FCS_MODE_TC : FCS_MODE_GEMV;
+    if (use_mode == FCS_MODE_AUTO) use_mode = auto_prefers_tc(db, nq, k, mask_on) ? FCS_MODE_TC : FCS_MODE_GEMV;
     if (use_mode == FCS_MODE_TC && mask_on)
         return fail(FCS_ERR_UNSUPPORTED, "FCS_MODE_TC does not apply the coverage mask (the faiss flavour has none, dbsearch.py:307-310)");
     if (use_mode == FCS_MODE_TC && k > tc_max_k())
@@ -461,8 +474,7 @@ extern "C" int fcs_search(fcs_db* db, const float* q, int nq, const int32_t* qle
     // Small exact-scan searches (the per-query loop of the reference's torch flavour) run zero-copy: the kernel
     // reads the queries from, and writes the k results to, pinned host memory (UVA), so the call is one launch
     // plus one stream synchronisation instead of launch + three copies.
-    const bool gemv = mode == FCS_MODE_GEMV || (mode == FCS_MODE_AUTO && !(db->tc && nq >= tc_min_batch() && k <= tc_max_k() &&
-                                                                          !(qlen != nullptr && db->lens != nullptr)));
+    const bool gemv = mode == FCS_MODE_GEMV || (mode == FCS_MODE_AUTO && !auto_prefers_tc(db, nq, k, qlen != nullptr && db->lens != nullptr));
     if (gemv && k <= GEMV_MAX_K && nq <= 64) {
         rc = search_core(db, db->h_q, nq, qlen, mincov, k, qnorm, FCS_MODE_GEMV, kprime, db->h_scores, db->h_ids, db->h_keys, db->stream);
         if (rc != FCS_OK) return rc;

@@ -98,10 +98,15 @@ def test_candidate_overflow_falls_back_to_exact_scan():
 
 
 def test_auto_mode_picks_paths():
-    db = synth.host_db(3000, base_seed=71)
+    """AUTO compares a cost estimate of the two paths: small batches and small databases scan, big ones use tcgen05."""
+    db = synth.host_db(300000, base_seed=71)
     h = _db(db)
     h.search(synth.host_queries(2, 1, normalise=True), 5)
     assert h.timing().last_mode == native.MODE_GEMV
-    h.search(synth.host_queries(64, 1, normalise=True), 5)
+    h.search(synth.host_queries(512, 1, normalise=True), 5)
     assert h.timing().last_mode == native.MODE_TC
     h.close()
+    small = _db(synth.host_db(3000, base_seed=72))
+    small.search(synth.host_queries(64, 1, normalise=True), 5)  # 8 scan launches beat the TC path's fixed cost
+    assert small.timing().last_mode == native.MODE_GEMV
+    small.close()
