@@ -118,3 +118,22 @@ def test_config4_ted_slice_45m_rows_per_gpu():
     _agree(s[sample], i[sample], s2, i2, tol=2e-6)
     assert h.timing().last_mode == native.MODE_GEMV
     h.close()
+
+
+def test_config5_style_proteome_batch_65536_queries_k50():
+    """BASELINE configs[4] shape in the batch dimension (65 536 queries, k=50) against a 2 M-row shard: 128 query
+    groups, 2 GB of candidate buffers -- the plumbing the 8-GPU proteome-wide search needs on every rank."""
+    dev = torch.device("cuda:0")
+    n, nq, k = 2_000_000, 65_536, 50
+    h, rows = _build(n, dev, True, [17])
+    g = torch.Generator(dev).manual_seed(5)
+    q = torch.nn.functional.normalize(torch.randn(nq, 128, device=dev, generator=g)).cpu().numpy()
+    q[40000] = rows[17]
+    s, i = h.search(q, k, mode=native.MODE_TC)
+    assert h.timing().last_mode == native.MODE_TC and h.timing().last_tc_fallbacks <= 64
+    assert i[40000, 0] == 17 and abs(s[40000, 0] - 1.0) < 1e-5
+    assert (np.diff(s, axis=1) <= 0).all() and (i >= 0).all() and (i < n).all()
+    sample = np.array([0, 511, 512, 40000, 65535, 33333, 12345, 60000])
+    s2, i2 = h.search(q[sample], k, mode=native.MODE_GEMV)
+    _agree(s[sample], i[sample], s2, i2, tol=2e-6)
+    h.close()
