@@ -463,7 +463,7 @@ __global__ void __launch_bounds__(128) tc_select_warp_kernel(uint64_t* __restric
             const uint32_t c = T | (1u << bit);
             int ge = 0;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) ge += (key[j] != 0ull && uint32_t(key[j] >> 32) >= c) ? 1 : 0;
+            for (int j = 0; j < 32; ++j) ge += (uint32_t(key[j] >> 32) >= c) ? 1 : 0;  // empty slots have score word 0 < c
             if (__reduce_add_sync(FULL, ge) >= kprime) T = c;
         }
     }
@@ -717,6 +717,12 @@ int tc_create(TcState** out, int device, int sm_count, const float* rows, int64_
     auto run = [&]() -> int {
         TC_CUDA(cudaFuncSetAttribute(tc_gemm_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
         TC_CUDA(cudaFuncSetAttribute(tc_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_CAP * 8));
+        // the small kernels between two GEMM launches ask for the same shared-memory carve-out as the GEMM kernel,
+        // so the SMs are not reconfigured (drained) twice per round
+        TC_CUDA(cudaFuncSetAttribute(tc_select_warp_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        TC_CUDA(cudaFuncSetAttribute(tc_select_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        TC_CUDA(cudaFuncSetAttribute(tc_prep_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        TC_CUDA(cudaFuncSetAttribute(tc_rescore_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         for (cudaEvent_t& e : s->ev) TC_CUDA(cudaEventCreate(&e));
         TC_CUDA(cudaMalloc(&s->b_img, size_t(s->n_tiles) * B_TILE_BYTES));
         TC_CUDA(cudaMalloc(&s->n_flagged, 2 * sizeof(unsigned)));
