@@ -34,19 +34,6 @@ def shard_ranges(n_rows: int, n_shards: int) -> List[Tuple[int, int]]:
     return [(min(n_rows, g * per), min(n_rows, (g + 1) * per)) for g in range(n_shards)]
 
 
-def merge_keys_host(keys: np.ndarray, k: int) -> Tuple[np.ndarray, np.ndarray]:
-    """Reference merge of packed key lists on the host: keys [n_lists, nq, k] -> (scores, ids).
-
-    Used only by the CPU (gloo) tests of the multi-rank plumbing and as documentation of the key
-    format: high 32 bits = order-preserving image of the fp32 score, low 32 bits = 0xFFFFFFFF - id.
-    """
-    keys = np.asarray(keys, dtype=np.uint64)
-    n_lists, nq, kk = keys.shape
-    flat = np.transpose(keys, (1, 0, 2)).reshape(nq, n_lists * kk)
-    top = np.sort(flat, axis=1)[:, ::-1][:, :k]  # descending, unsigned
-    return decode_keys(top)
-
-
 def encode_keys(scores: np.ndarray, ids: np.ndarray) -> np.ndarray:
     s = np.ascontiguousarray(scores, dtype=np.float32).view(np.uint32).astype(np.uint64)
     neg = (s & np.uint64(0x80000000)) != 0

@@ -10,6 +10,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from merizo_search_b200 import engine, synth
+from host_merge import merge_keys_host
 from oracle import foldclass_oracle as orc
 
 N, NQ, K = 5001, 7, 9
@@ -36,7 +37,7 @@ def _worker(rank, world, port, out_dir, q_groups):
             return torch.from_numpy(engine.encode_keys(D, np.where(I >= 0, I + lo, -1)).view(np.int64))
 
         def merge(gathered, k):
-            return engine.merge_keys_host(gathered.numpy().view(np.uint64), k)
+            return merge_keys_host(gathered.numpy().view(np.uint64), k)
 
         s, i = eng.search(q, K, local_search=local_search, merge=merge)
         np.save(os.path.join(out_dir, f"s{rank}.npy"), s)

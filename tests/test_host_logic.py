@@ -7,6 +7,7 @@ import pytest
 import torch
 
 from merizo_search_b200 import engine, faiss_driver, synth
+from host_merge import merge_keys_host
 from oracle import foldclass_oracle as orc
 
 
@@ -47,7 +48,7 @@ def test_host_merge_equals_oracle_topk():
     for lo, hi in engine.shard_ranges(9000, 4):
         D, I = orc.knn_exact_blockwise(q, orc.db_iterator(db[lo:hi], 1000), k)
         parts.append(engine.encode_keys(D, I + lo))
-    s, i = engine.merge_keys_host(np.stack(parts), k)
+    s, i = merge_keys_host(np.stack(parts), k)
     D, I = orc.knn_exact_blockwise(q, orc.db_iterator(db, 262144), k)
     full = orc.all_scores_ip(q, db)
     for r in range(5):
