@@ -85,6 +85,12 @@ struct fcs_db {
     float* h_scores = nullptr;
     int64_t* h_ids = nullptr;
     uint64_t* h_keys = nullptr;  // only for the zero-copy small-result path
+    // exact-scan fallback of flagged tensor-core queries (gathered queries, gathered results)
+    float* fb_q = nullptr;
+    uint64_t* fb_keys = nullptr;
+    float* fb_scores = nullptr;
+    int64_t* fb_ids = nullptr;
+    size_t fb_cap = 0;
     size_t h_out_cap = 0;
 
     void* h_stage[2] = {nullptr, nullptr};
@@ -225,6 +231,10 @@ extern "C" int fcs_db_destroy(fcs_db* db) {
     cudaFree(db->d_keys);
     cudaFree(db->d_scores);
     cudaFree(db->d_ids);
+    cudaFree(db->fb_q);
+    cudaFree(db->fb_keys);
+    cudaFree(db->fb_scores);
+    cudaFree(db->fb_ids);
     if (db->h_q) cudaFreeHost(db->h_q);
     if (db->h_scores) cudaFreeHost(db->h_scores);
     if (db->h_ids) cudaFreeHost(db->h_ids);
@@ -396,6 +406,41 @@ static int gemv_search(fcs_db* db, const float* q, int nq, const int32_t* qlen, 
     return FCS_OK;
 }
 
+// Re-run the flagged queries of a tensor-core search on the exact fp32 scan.
+static int exact_fallback(fcs_db* db, const float* q_dev, int nq, const unsigned* flagged, int k, int qnorm, float* out_scores,
+                          int64_t* out_ids, uint64_t* out_keys, cudaStream_t stream, int* launches) {
+    int nf = 0;
+    for (int q = 0; q < nq; ++q) nf += (flagged[q] & 3u) ? 1 : 0;
+    if (nf == 0) return FCS_OK;
+    if (db->fb_cap < size_t(nf)) {
+        cudaFree(db->fb_q); cudaFree(db->fb_keys); cudaFree(db->fb_scores); cudaFree(db->fb_ids);
+        db->fb_q = nullptr; db->fb_keys = nullptr; db->fb_scores = nullptr; db->fb_ids = nullptr;
+        db->fb_cap = 0;
+        FCS_CUDA(cudaMalloc(&db->fb_q, size_t(nf) * DIM * sizeof(float)));
+        FCS_CUDA(cudaMalloc(&db->fb_keys, size_t(nf) * FCS_MAX_K * sizeof(uint64_t)));
+        FCS_CUDA(cudaMalloc(&db->fb_scores, size_t(nf) * FCS_MAX_K * sizeof(float)));
+        FCS_CUDA(cudaMalloc(&db->fb_ids, size_t(nf) * FCS_MAX_K * sizeof(int64_t)));
+        db->fb_cap = size_t(nf);
+    }
+    int j = 0;
+    for (int q = 0; q < nq; ++q)
+        if (flagged[q] & 3u)
+            FCS_CUDA(cudaMemcpyAsync(db->fb_q + size_t(j++) * DIM, q_dev + size_t(q) * DIM, DIM * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+    int rc = gemv_search(db, db->fb_q, nf, nullptr, 0.f, k, qnorm, db->fb_scores, db->fb_ids, db->fb_keys, stream, launches);
+    if (rc != FCS_OK) return rc;
+    j = 0;
+    for (int q = 0; q < nq; ++q) {
+        if (!(flagged[q] & 3u)) continue;
+        FCS_CUDA(cudaMemcpyAsync(out_keys + size_t(q) * k, db->fb_keys + size_t(j) * k, size_t(k) * sizeof(uint64_t), cudaMemcpyDeviceToDevice, stream));
+        if (out_scores)
+            FCS_CUDA(cudaMemcpyAsync(out_scores + size_t(q) * k, db->fb_scores + size_t(j) * k, size_t(k) * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+        if (out_ids)
+            FCS_CUDA(cudaMemcpyAsync(out_ids + size_t(q) * k, db->fb_ids + size_t(j) * k, size_t(k) * sizeof(int64_t), cudaMemcpyDeviceToDevice, stream));
+        ++j;
+    }
+    return FCS_OK;
+}
+
 // AUTO: the batched tensor-core path pays a fixed ~0.4 ms (threshold warm-up rounds, selection launches) and then
 // ~256 flop per (query,row) at ~1.1 PFLOP/s; the exact scan streams 512 B per row once per 8 queries at ~6.5 TB/s
 // with ~10 us per launch.  Pick the cheaper estimate.
@@ -429,12 +474,9 @@ static int search_core(fcs_db* db, const float* q_dev, int nq, const int32_t* ql
         const unsigned* flagged = nullptr;
         rc = tc_search(db->tc, q_dev, nq, k, kprime, qnorm, out_scores, out_ids, out_keys, stream, &launches, &flagged, &fallbacks);
         if (rc != FCS_OK) return fail(rc, "tensor-core search failed: %s", tc_last_error());
-        // queries whose exactness certificate failed (or whose candidate buffer overflowed): exact scan
-        for (int q = 0; q < nq && fallbacks > 0 && rc == FCS_OK; ++q) {
-            if ((flagged[q] & 3u) == 0u) continue;
-            rc = gemv_search(db, q_dev + size_t(q) * DIM, 1, nullptr, 0.f, k, qnorm, out_scores ? out_scores + size_t(q) * k : nullptr,
-                             out_ids ? out_ids + size_t(q) * k : nullptr, out_keys + size_t(q) * k, stream, &launches);
-        }
+        // queries whose exactness certificate failed (or whose candidate buffer overflowed): exact scan, 8 queries
+        // per pass over the shard (gathered into a contiguous buffer, results scattered back)
+        if (fallbacks > 0) rc = exact_fallback(db, q_dev, nq, flagged, k, qnorm, out_scores, out_ids, out_keys, stream, &launches);
     }
     if (rc != FCS_OK) return rc;
     if (db->profiling) FCS_CUDA(cudaEventRecord(db->ev1, stream));

@@ -70,10 +70,12 @@ def test_certificate_failure_falls_back_to_exact_scan():
     base = db[123].copy()
     dup = base[None, :] + 2e-4 * rng.standard_normal((6000, 128)).astype(np.float32)
     db[5000:11000] = dup / np.linalg.norm(dup, axis=1, keepdims=True)
-    q = np.stack([base] + [synth.host_queries(1, 52 + j, normalise=True)[0] for j in range(39)]).astype(np.float32)
+    # 20 queries inside the duplicate cluster (more than one 8-query fallback pass), 20 ordinary ones
+    q = np.stack([db[5000 + 37 * j] for j in range(20)] + [synth.host_queries(1, 52 + j, normalise=True)[0] for j in range(20)])
+    q = np.ascontiguousarray(q, dtype=np.float32)
     h = _db(db)
     s, i = h.search(q, k, mode=native.MODE_TC)
-    assert h.timing().last_tc_fallbacks >= 1
+    assert h.timing().last_tc_fallbacks >= 10
     D, I = orc.knn_exact_blockwise(q, orc.db_iterator(db, 262144), k)
     full = orc.all_scores_ip(q, db)
     for r in range(q.shape[0]):
