@@ -25,6 +25,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC",
+    "-Xcompiler", "-pthread",
     "-cudart", "static",
 ] + (["-DFCS_TC_TRACE"] if os.environ.get("FCS_TC_TRACE") else [])
 
@@ -95,7 +96,7 @@ def _build_locked(verbose: bool) -> str:
             failed.append(src)
     if failed:
         raise RuntimeError(f"nvcc failed for: {', '.join(failed)}")
-    link = [nvcc, "-shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH, *objs]
+    link = [nvcc, "-shared", "-Xcompiler", "-pthread", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH, *objs]
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout)

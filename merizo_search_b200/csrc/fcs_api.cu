@@ -5,6 +5,8 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <thread>
+#include <vector>
 
 #include "fcs_common.cuh"
 #include "fcs_internal.h"
@@ -47,6 +49,26 @@ struct DeviceGuard {
     }
 };
 constexpr size_t STAGE_BYTES_HOST = size_t(32) << 20;  // pinned staging buffers for fcs_db_upload
+
+// pageable (or memory-mapped) -> pinned staging copy; one thread tops out near 10 GB/s, well under a PCIe 5 x16 link
+void parallel_memcpy(void* dst, const void* src, size_t bytes) {
+    unsigned hw = std::thread::hardware_concurrency();
+    const size_t nthreads = bytes < (size_t(4) << 20) ? 1 : (hw >= 8 ? 4 : (hw >= 4 ? 2 : 1));
+    if (nthreads == 1) {
+        memcpy(dst, src, bytes);
+        return;
+    }
+    const size_t per = ((bytes / nthreads) + 4095) & ~size_t(4095);
+    std::vector<std::thread> pool;
+    for (size_t t = 1; t < nthreads; ++t) {
+        const size_t off = t * per;
+        if (off >= bytes) break;
+        const size_t len = (off + per < bytes) ? per : (bytes - off);
+        pool.emplace_back([=] { memcpy(static_cast<char*>(dst) + off, static_cast<const char*>(src) + off, len); });
+    }
+    memcpy(dst, src, per < bytes ? per : bytes);
+    for (auto& th : pool) th.join();
+}
 
 }  // namespace
 
@@ -294,7 +316,7 @@ extern "C" int fcs_db_upload(fcs_db* db, int64_t row0, int64_t n, const float* h
         const int b = db->stage_next;
         db->stage_next ^= 1;
         FCS_CUDA(cudaEventSynchronize(db->stage_ev[b]));
-        memcpy(db->h_stage[b], host_rows + r * DIM, size_t(cnt) * ROW_BYTES);
+        parallel_memcpy(db->h_stage[b], host_rows + r * DIM, size_t(cnt) * ROW_BYTES);
         FCS_CUDA(cudaMemcpyAsync(db->rows + (row0 + r) * DIM, db->h_stage[b], size_t(cnt) * ROW_BYTES, cudaMemcpyHostToDevice,
                                  db->stream));
         FCS_CUDA(cudaEventRecord(db->stage_ev[b], db->stream));

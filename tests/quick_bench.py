@@ -39,6 +39,23 @@ def run(n, nq, k, iters=50):
     print(f"n={n} nq={nq} k={k}: {ms*1e3:.1f} us/launch  {gbs:.0f} GB/s ({gbs/6452.8*100:.1f}% of measured HBM)  e2e host call {e2e*1e3:.1f} us", flush=True)
     h.close()
 
-if __name__ == "__main__":
+if __name__ == "__main__" and len(sys.argv) == 1:
     for n, nq, k in [(500000, 1, 10), (500000, 1, 100), (500000, 2, 10), (500000, 4, 10), (500000, 8, 10), (500000, 8, 100), (4000000, 1, 10), (4000000, 8, 10), (40000000, 1, 10)]:
         run(n, nq, k)
+
+
+def upload_speed(n=4_000_000):
+    """Host -> device load rate of fcs_db_upload (pageable numpy rows through the pinned staging ring)."""
+    x = np.random.default_rng(0).standard_normal((n, 128), dtype=np.float32)
+    h = native.Database(n)
+    t0 = time.perf_counter()
+    for r0 in range(0, n, 262144):
+        h.upload(r0, x[r0:r0 + 262144])
+    h.finalize()
+    dt = time.perf_counter() - t0
+    print(f"upload+finalize {n} rows ({n*512/1e9:.2f} GB): {dt:.3f} s = {n*512/1e9/dt:.1f} GB/s", flush=True)
+    h.close()
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "upload":
+    upload_speed()
