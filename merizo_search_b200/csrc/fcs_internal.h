@@ -50,6 +50,5 @@ cudaError_t lengths_to_u16_launch(const int32_t* lens, uint16_t* out, int64_t n,
 // ------------------------------------------------------------------ merge kernel (fcs_merge.cu)
 cudaError_t merge_topk_launch(const uint64_t* keys, int n_lists, int nq, int k, float* out_scores, int64_t* out_ids,
                               uint64_t* out_keys, cudaStream_t stream);
-cudaError_t decode_keys_launch(const uint64_t* keys, int64_t n, float* out_scores, int64_t* out_ids, cudaStream_t stream);
 
 }  // namespace fcs

@@ -58,16 +58,6 @@ __global__ void __launch_bounds__(256) merge_topk_kernel(const uint64_t* __restr
     }
 }
 
-__global__ void __launch_bounds__(256) decode_keys_kernel(const uint64_t* __restrict__ keys, int64_t n,
-                                                          float* __restrict__ out_scores, int64_t* __restrict__ out_ids) {
-    const int64_t stride = int64_t(gridDim.x) * blockDim.x;
-    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const uint64_t key = keys[i];
-        if (out_scores) out_scores[i] = key_score(key);
-        if (out_ids) out_ids[i] = key_id(key);
-    }
-}
-
 }  // namespace
 
 cudaError_t merge_topk_launch(const uint64_t* keys, int n_lists, int nq, int k, float* out_scores, int64_t* out_ids,
@@ -77,14 +67,6 @@ cudaError_t merge_topk_launch(const uint64_t* keys, int n_lists, int nq, int k, 
     int64_t g = (total + 255) / 256;
     if (g > 148 * 8) g = 148 * 8;
     merge_topk_kernel<<<int(g), 256, 0, stream>>>(keys, n_lists, nq, k, out_scores, out_ids, out_keys);
-    return cudaGetLastError();
-}
-
-cudaError_t decode_keys_launch(const uint64_t* keys, int64_t n, float* out_scores, int64_t* out_ids, cudaStream_t stream) {
-    if (n <= 0) return cudaSuccess;
-    int64_t g = (n + 255) / 256;
-    if (g > 148 * 8) g = 148 * 8;
-    decode_keys_kernel<<<int(g), 256, 0, stream>>>(keys, n, out_scores, out_ids);
     return cudaGetLastError();
 }
 
