@@ -663,7 +663,7 @@ struct TcState {
     unsigned* n_flagged = nullptr;
     unsigned* h_n_flagged = nullptr;  // pinned
     unsigned* h_flags = nullptr;      // pinned, nq_cap
-    double growth = 3.0;
+    double growth = 2.0;  // rows seen grow x3 per round; measured best on B200 (profiles/r01_ncu_summary.md)
     bool verbose = false;
     // timing of the dominant kernel: one event pair per K3 launch of the last search
     static constexpr int MAX_ROUNDS = 48;
