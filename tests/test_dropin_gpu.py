@@ -1,6 +1,5 @@
 """GPU: the reference-facing Python layer (merizo_search_b200.dbsearch / faiss_driver) against the oracle."""
 import pickle
-import types
 
 import numpy as np
 import pytest
@@ -50,11 +49,6 @@ def test_read_database_and_search_pt_flavour(pt_db):
         b200.search_query_against_db({"embedding": emb, "seq": "G" * 100}, target, 0.7, len(index) + 1)
 
 
-def test_read_database_missing_exits():
-    with pytest.raises(SystemExit):
-        b200.read_database("/nonexistent/db", "cuda")
-
-
 def test_knn_exact_block_iterator():
     db = synth.host_db(30000, base_seed=58)
     xq = orc.normalize_queries(torch.from_numpy(synth.host_queries(9, 59)))
@@ -100,10 +94,3 @@ def test_dbsearch_faiss_driver_skip_tmalign(tiny_faiss_db, tmp_path):
         assert h["query"] == f"query{[4, 17, 33][q]}" and h["tmalign_output"] is None and h["dom_str"] == "1-10"
     assert results[0][0]["dbindex"] == 4 and results[1][0]["dbindex"] == 17 and results[2][0]["dbindex"] == 33
     b200.release_all()
-
-
-def test_install_patches_reference_module():
-    ref = types.SimpleNamespace(read_database=None, search_query_against_db=None, dbsearch_faiss=None)
-    out = b200.install(ref)
-    assert out.read_database is b200.read_database and out.search_query_against_db is b200.search_query_against_db
-    assert out.dbsearch_faiss is faiss_driver.dbsearch_faiss
