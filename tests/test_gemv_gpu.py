@@ -99,6 +99,28 @@ def test_many_query_groups_back_to_back():
     h.close()
 
 
+def test_exact_ties_are_ordered_by_ascending_id():
+    """Duplicate rows tie exactly; torch/faiss leave the order unspecified, this library returns ascending ids."""
+    n, k = 5000, 12
+    db = synth.host_db(n, base_seed=19)
+    dup = [4000, 17, 2500, 999, 3]
+    for r in dup[1:]:
+        db[r] = db[dup[0]]
+    q = db[dup[0]].copy()
+    for keep_bf16, mode in ((False, native.MODE_GEMV), (True, native.MODE_TC)):
+        h = native.Database(n, keep_bf16=keep_bf16)
+        h.upload(0, db)
+        h.finalize()
+        qs = np.stack([q] + [synth.host_queries(1, 90 + j, normalise=True)[0] for j in range(39)]).astype(np.float32)
+        s, i = h.search(qs, k, mode=mode)
+        assert i[0, :5].tolist() == sorted(dup) and np.allclose(s[0, :5], 1.0, atol=1e-6)
+        D, I = orc.knn_exact_blockwise(qs, orc.db_iterator(db, 262144), k)
+        full = orc.all_scores_ip(qs, db)
+        for r in range(qs.shape[0]):
+            orc.check_topk(s[r], i[r], D[r], I[r], full[r], tol=TOL)
+        h.close()
+
+
 def test_all_rows_masked_gives_zero_scores():
     n = 2000
     db = synth.host_db(n, base_seed=5, normalise=False)
