@@ -7,6 +7,7 @@ Workloads (BASELINE.json `configs`, synthetic unit-norm 128-d rows, random queri
   cfg3 (default)  10 M rows, 4096-query batch, k=100      -- tcgen05 path; largest single-GPU config
   cfg2            500 k rows (CATH scale), 1 query, k=10  -- fp32 scan (GEMV) path, coverage mask on
   cfg4            45.625 M rows PER GPU (365 M / 8), 1 query, k=10 -- fp32 scan, TED-scale slice
+  cfg4b           the same slice, 1024-query batch, k=10          -- tcgen05 path
 With N>1 the database of cfg2/cfg3 is row-sharded over the ranks (strong scaling); cfg4 keeps
 45.625 M rows per rank (weak scaling; at N=8 it is the full 365 M-row TED database).  The per-rank
 key lists are exchanged with ONE NCCL all-gather and merged on the GPU.
@@ -41,6 +42,8 @@ WORKLOADS = {
                  desc="BASELINE configs[2]: synthetic 10M x 128 DB, 4096-query batch, k=100, tcgen05 path"),
     "cfg4": dict(rows=45_625_000, nq=1, k=10, mode="gemv", mask=False, scaling="weak",
                  desc="BASELINE configs[3] slice: 365M/8 = 45.625M x 128 fp32 rows per GPU, single query, k=10, fp32 scan path"),
+    "cfg4b": dict(rows=45_625_000, nq=1024, k=10, mode="tc", mask=False, scaling="weak",
+                  desc="BASELINE configs[3] slice: 365M/8 = 45.625M x 128 rows per GPU, 1024-query batch, k=10, tcgen05 path"),
 }
 DEFAULT_WORKLOAD = "cfg3"
 
@@ -192,6 +195,8 @@ def run_gpu(args, wl, wl_name, steps=None, warmup=None):
     qg = args.query_groups
     if world == 1:
         qg = 1
+    elif wl["scaling"] == "weak":
+        qg = 1  # the TED-scale slices are the row-sharded configuration of the metric: never replicate them
     elif qg <= 0:
         qg = DistributedEngine.auto_query_groups(rows_total, world, bytes_per_row=514 + (256 if wl["mode"] == "tc" else 0))
     while qg > 1 and (world % qg != 0 or qg > nq):
@@ -371,7 +376,7 @@ def main():
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.steps <= 0:  # long enough (>= ~0.2 s) for nvidia-smi to sample clocks inside the timed region
-        args.steps = {"cfg3": 20, "cfg2": 4000, "cfg4": 60}[args.workload]
+        args.steps = {"cfg3": 20, "cfg2": 4000, "cfg4": 60, "cfg4b": 10}[args.workload]
     if args.warmup <= 0:
         args.warmup = 3 if wl["mode"] == "tc" else 10
     args.warmup = max(args.warmup, 3)
@@ -404,10 +409,10 @@ def main():
     # slice (the full database at N=8); cfg2 is the CATH-scale single-query case (1 GPU only).
     extra = {}
     if not args.no_extra:
-        others = [w for w in (("cfg4", "cfg2") if world == 1 else ("cfg4",)) if w != args.workload]
+        others = [w for w in (("cfg4", "cfg4b", "cfg2") if world == 1 else ("cfg4", "cfg4b")) if w != args.workload]
         for w in others:
             try:
-                o, _ = run_gpu(args, WORKLOADS[w], w, steps={"cfg4": 40, "cfg2": 2000, "cfg3": 10}[w], warmup=5)
+                o, _ = run_gpu(args, WORKLOADS[w], w, steps={"cfg4": 40, "cfg4b": 8, "cfg2": 2000, "cfg3": 10}[w], warmup=5)
                 if rank == 0:
                     extra[w] = {key: o[key] for key in ("value", "unit", "ms_per_step", "scaling", "e2e", "roofline", "config", "gpu_launches")}
             except Exception as exc:  # an extra must never take the primary line down

@@ -1,10 +1,11 @@
 mkdir -p gpurun_out
-for g in 1.5 2; do
-  for rows in 10000000 1250000; do
-    FCS_TC_GROWTH=$g timeout 300 python bench.py --workload cfg3 --rows $rows --steps 8 --warmup 3 --no-cpu-baseline --no-extra 2>/dev/null | python -c "
-import json,sys
-d=json.loads(sys.stdin.read().strip().splitlines()[-1])
-print('growth $g rows $rows: %.3f ms/step  %.0f q/s  K3 frac %.3f  fallbacks %d' % (d['ms_per_step'], d['value'], d['roofline']['frac'], d['config']['tc_fallback_queries']))
-"
-  done
-done
+SECONDS=0
+timeout 900 python bench.py --no-cpu-baseline > gpurun_out/bench_default2.json 2> gpurun_out/bench_default2.err
+echo "exit $? in ${SECONDS}s"; tail -2 gpurun_out/bench_default2.err
+python - <<PY
+import json
+d=json.load(open("gpurun_out/bench_default2.json"))
+print("primary", d["config"]["workload"], "%.0f q/s" % d["value"], "frac %.3f" % d["roofline"]["frac"], "e2e %.0f" % d["e2e"]["value"])
+for k,v in d["extra"].items():
+    print(" extra", k, ("%.1f q/s ms %.3f frac %.3f e2e %.1f fb %s" % (v["value"], v["ms_per_step"], v["roofline"]["frac"], v["e2e"]["value"], v["config"]["tc_fallback_queries"])) if "value" in v else v)
+PY
