@@ -362,6 +362,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_filter_kernel(const TcG
                 tc_fence_after();
                 TRACE(2, it, blockIdx.x == 0 && warp == 5 && lane == 0);
                 const int64_t row_base = (p.tile0 + ti + j) * TC_N;
+                int pend_n = 0;
+                uint32_t pend_v0 = 0, pend_v1 = 0;
+                int64_t pend_r0 = 0, pend_r1 = 0;
                 // Fast path: 32 scores per tcgen05.ld, reduced with 3-input max, one compare against the
                 // threshold.  Slow path (some lane of the warp has a hit in an 8-column group): the group is
                 // re-read from TMEM into 8 fixed registers and handled by ONE compact, warp-uniform loop.  Keep
@@ -402,7 +405,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_filter_kernel(const TcG
                                 uint32_t bits = v8[0];
 #pragma unroll
                                 for (int cc = 1; cc < 8; ++cc) bits = (c == cc) ? v8[cc] : bits;
-                                tc_append(p, res, q, __uint_as_float(bits), row_base + part * 32 + g * 8 + c);
+                                const int64_t hit_row = row_base + part * 32 + g * 8 + c;
+                                // park up to two hits in registers: they are appended after the accumulator has been
+                                // handed back to the MMA issuer (the append's atomics/stores are off the critical path)
+                                if (pend_n == 0) {
+                                    pend_v0 = bits;
+                                    pend_r0 = hit_row;
+                                    pend_n = 1;
+                                } else if (pend_n == 1) {
+                                    pend_v1 = bits;
+                                    pend_r1 = hit_row;
+                                    pend_n = 2;
+                                } else {
+                                    tc_append(p, res, q, __uint_as_float(bits), hit_row);
+                                }
                             }
                         }
                     }
@@ -411,6 +427,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_filter_kernel(const TcG
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tmem_empty[t]);
+                if (pend_n > 0) tc_append(p, res, q, __uint_as_float(pend_v0), pend_r0);
+                if (pend_n > 1) tc_append(p, res, q, __uint_as_float(pend_v1), pend_r1);
                 TRACE(4, it, blockIdx.x == 0 && warp == 5 && lane == 0);
             }
             if (!p.first_round) tc_close_reservation(p, res, q);
