@@ -368,13 +368,16 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=os.environ.get("FCS_BENCH_WORKLOAD", DEFAULT_WORKLOAD), choices=sorted(WORKLOADS))
     ap.add_argument("--rows", type=int, default=0, help="override the total row count (debugging)")
+    ap.add_argument("--nq", type=int, default=0, help="override the batch size (debugging)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the ride-along workloads (cfg4, cfg2)")
     ap.add_argument("--query-groups", type=int, default=0,
                     help="N>1: ranks = row shards x query groups; 0 = auto (replicate the database as far as ~80 GB per "
                          "GPU allow and split the batch), 1 = pure row sharding")
     args = ap.parse_args()
-    wl = WORKLOADS[args.workload]
+    wl = dict(WORKLOADS[args.workload])
+    if args.nq:
+        wl["nq"] = args.nq
     if args.steps <= 0:  # long enough (>= ~0.2 s) for nvidia-smi to sample clocks inside the timed region
         args.steps = {"cfg3": 20, "cfg2": 4000, "cfg4": 60, "cfg4b": 10}[args.workload]
     if args.warmup <= 0:

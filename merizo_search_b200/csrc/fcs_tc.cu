@@ -54,7 +54,7 @@ constexpr int A_TILE_BYTES = TC_M * DIM * 2;     // 32 KB
 constexpr int B_TILE_BYTES = TC_N * DIM * 2;     // 32 KB
 constexpr int TC_STAGES = 3;
 constexpr int TC_PREFETCH = 6;                     // DB tiles prefetched into L2 ahead of the ring
-constexpr int TC_RES = 16;                        // candidate slots reserved per atomic
+constexpr int TC_RES_MAX = 16;                    // candidate slots reserved per atomic (upper bound, see res_block)
 constexpr int TC_MMA_WARPS = 4;                   // MMA-issuing warps (one thread each), one query tile apiece
 constexpr int TC_THREADS = (1 + TC_MMA_WARPS + 16) * 32;  // producer + MMA issuers + 16 epilogue warps
 constexpr int TC_CAP = 4096;                     // candidate slots per query
@@ -197,6 +197,7 @@ struct TcGemmParams {
     uint64_t* cand;        // [nq][TC_CAP] approximate keys (score, LOCAL row); 0 = unused reserved slot
     int first_round;       // thresholds are all -inf and tile0 == 0: slot = row, no atomics
     int trace_on;          // debug builds (FCS_TC_TRACE): record cycle stamps in this launch
+    int res_block;         // slots reserved per atomic: small when many CTAs share a query group (unused slots are waste)
 };
 
 #ifdef FCS_TC_TRACE
@@ -207,9 +208,9 @@ __device__ long long g_trace[5][256];
 #define TRACE(row, idx, cond) do { } while (0)
 #endif
 
-// Per-thread slot reservation: one atomic buys TC_RES slots of the query's buffer.
+// Per-thread slot reservation: one atomic buys p.res_block slots of the query's buffer.
 struct SlotRes {
-    unsigned base = 0, used = TC_RES;
+    unsigned base = 0, used = ~0u;  // ~0u: nothing reserved yet
 };
 __device__ __forceinline__ void tc_append(const TcGemmParams& p, SlotRes& res, int q, float v, int64_t row) {
     if (row >= p.n_rows) return;  // zero padding rows of the last DB tile
@@ -217,8 +218,8 @@ __device__ __forceinline__ void tc_append(const TcGemmParams& p, SlotRes& res, i
     if (p.first_round) {
         slot = unsigned(row);
     } else {
-        if (res.used == TC_RES) {
-            res.base = atomicAdd(p.cnt + q, unsigned(TC_RES));
+        if (res.used >= unsigned(p.res_block)) {
+            res.base = atomicAdd(p.cnt + q, unsigned(p.res_block));
             res.used = 0;
         }
         slot = res.base + res.used++;
@@ -227,7 +228,8 @@ __device__ __forceinline__ void tc_append(const TcGemmParams& p, SlotRes& res, i
 }
 // unused slots of the last reservation must read as empty
 __device__ __forceinline__ void tc_close_reservation(const TcGemmParams& p, SlotRes& res, int q) {
-    for (; res.used < TC_RES; ++res.used) {
+    if (res.used == ~0u) return;  // this thread never appended
+    for (; res.used < unsigned(p.res_block); ++res.used) {
         const unsigned slot = res.base + res.used;
         if (slot < unsigned(TC_CAP)) p.cand[size_t(q) * TC_CAP + slot] = 0ull;
     }
@@ -835,6 +837,12 @@ int tc_search(TcState* s, const float* q_dev, int nq, int k, int kprime, int qno
         gp.trace_on = (getenv("FCS_TC_TRACE_ROUND") ? atoi(getenv("FCS_TC_TRACE_ROUND")) : 7) == rounds;
         const int64_t steps = int64_t(n_qgroups) * (t1 - seen);
         const int grid = int(steps < s->sm_count ? steps : s->sm_count);
+        {   // every thread that appends at all rounds its reservation up to res_block slots: keep the waste of the
+            // ~grid/n_qgroups segments that share a query below ~512 slots so the buffers stay in the warp-select range
+            const int segs = (grid + n_qgroups - 1) / n_qgroups + 1;
+            int rb = 512 / segs;
+            gp.res_block = rb < 2 ? 2 : (rb > TC_RES_MAX ? TC_RES_MAX : rb);
+        }
         const bool timed = rounds < TcState::MAX_ROUNDS;
         if (timed) TC_CUDA(cudaEventRecord(s->ev[2 * rounds], stream));
         tc_gemm_filter_kernel<<<grid, TC_THREADS, TC_SMEM, stream>>>(gp);
@@ -920,6 +928,7 @@ int tc_debug_approx(TcState* s, const float* q_dev, int nq, int qnorm, float* ou
     TC_CUDA(cudaGetLastError());
     TcGemmParams gp = {};
     gp.first_round = 1;
+    gp.res_block = TC_RES_MAX;
     gp.a_img = s->a_img; gp.b_img = s->b_img; gp.n_rows = s->n_rows; gp.nq = nq; gp.n_qgroups = n_qgroups;
     gp.thr = s->thr; gp.cnt = s->cnt; gp.cand = s->cand; gp.tile0 = 0; gp.tile1 = s->n_tiles;
     const int64_t steps = int64_t(n_qgroups) * s->n_tiles;
