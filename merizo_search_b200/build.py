@@ -20,7 +20,7 @@ INCLUDE = os.path.join(os.path.dirname(PKG_DIR), "include")
 LIB_PATH = os.path.join(PKG_DIR, "libfcsearch.so")
 STAMP_PATH = os.path.join(PKG_DIR, ".libfcsearch.stamp")
 
-SOURCES = ["fcs_api.cu", "fcs_gemv.cu", "fcs_loader.cu", "fcs_merge.cu", "fcs_tc.cu"]
+SOURCES = ["fcs_api.cu", "fcs_gemv.cu", "fcs_loader.cu", "fcs_merge.cu", "fcs_tc.cu", "fcs_embed.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
@@ -39,7 +39,7 @@ def _nvcc() -> str:
 
 def _source_hash() -> str:
     h = hashlib.sha256()
-    files = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))] + [os.path.join(INCLUDE, "fcsearch.h")]
+    files = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))] + [os.path.join(INCLUDE, f) for f in sorted(os.listdir(INCLUDE))]
     for f in files:
         with open(f, "rb") as fh:
             h.update(os.path.basename(f).encode())  # not the absolute path: the tree is copied to other machines

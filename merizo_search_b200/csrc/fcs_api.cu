@@ -26,6 +26,7 @@ static int fail(int code, const char* fmt, ...) {
     g_last_error = buf;
     return code;
 }
+void fcs::set_last_error(const char* msg) { g_last_error = msg ? msg : ""; }
 #define FCS_CUDA(call)                                                                                   \
     do {                                                                                                 \
         cudaError_t e__ = (call);                                                                        \

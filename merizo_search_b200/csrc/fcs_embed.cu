@@ -1,0 +1,767 @@
+// fcs_embed.cu -- batched FoldClassNet(128) forward: C-alpha traces -> 128-d embeddings (include/fcsembed.h).
+//
+// Replaces the one-structure-per-call torch forward of the reference (dbsearch.py:97-98, 287-301;
+// nndef_fold_egnn_embed.py:50-62; my_egnn_nocoords.py:44-74) for whole ragged batches.  Per EGNN layer:
+//
+//   edge_input_ij = [f_i, f_j, d_ij^2]                              (257)
+//   h_ij = SiLU(W1 edge_input_ij + b1)                              (514)     <- never materialised
+//   m_ij = SiLU(W2 h_ij + b2);  m_ij *= sigmoid(wg . m_ij + bg)     (256)     <- never materialised
+//   m_i  = sum_j m_ij;  f_i' = W4 SiLU(W3 [f_i, m_i] + b3) + b4 + f_i
+//
+// The reference materialises [L,L,257], [L,L,514] and [L,L,256] tensors in HBM per structure.  Here the first
+// linear layer is split algebraically,  W1 [f_i, f_j, d2] + b1 = P_i + Q_j + d2 * w_d  with
+// P = f W1[:, :128]^T + b1 and Q = f W1[:, 128:256]^T computed once per RESIDUE (K_e1), so the per-PAIR work
+// is one fused kernel (K_e2, embed_edge_kernel): h_ij is generated on the fly in shared memory, contracted
+// with W2 (the only O(L^2 x 514 x 256) term: 263 kFLOP per pair), gated and summed over j in registers /
+// shared memory; only m_i [L,256] is written.  HBM traffic per pair is ~0; the kernel is bound by the fp32
+// FMA pipe (packed FFMA2).  fp32 throughout: the embedding must match the reference network to fp32
+// rounding (tests: max relative error 5e-5 of the largest component, cosine > 1 - 1e-6).
+//
+//   K_e0 embed_init_feats_kernel   f = pe[:L]                          (PositionalEncoder.forward)
+//   K_e1 embed_node_proj_kernel    P, Q  [R, 528] (514 padded to 33 x 16)
+//   K_e2 embed_edge_kernel         m_i   [R, 256]   <- dominant: 2 * 528 * 256 flop per (i,j) pair
+//   K_e3 embed_node_mlp_kernel     f'    [R, 128]
+//   K_e4 embed_mean_kernel         mean over residues -> [n, 128]
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "../../include/fcsembed.h"
+#include "fcs_internal.h"
+
+namespace fcs {
+namespace {
+
+constexpr int EW = FCS_EMBED_WIDTH;    // 128
+constexpr int EH = FCS_EMBED_HIDDEN;   // 514
+constexpr int EHP = 528;               // hidden width padded to 33 chunks of 16 (pad weights are zero)
+constexpr int EM = FCS_EMBED_MDIM;     // 256
+constexpr int KC = 16;                 // hidden units per pipeline chunk
+constexpr int NCHUNK = EHP / KC;       // 33
+constexpr int TI = 8;                  // residues i per CTA
+constexpr int TJ = 16;                 // residues j per tile
+constexpr int TP = TI * TJ;            // 128 pairs per tile
+constexpr int EDGE_THREADS = 512;      // 16 warps: 4 (pair blocks of 32) x 4 (channel blocks of 64); thread = 8 pairs x 8 channels
+constexpr int QS = EHP + 1;            // shared-memory row stride of the Q tile (conflict-free column reads)
+
+// shared-memory carve-up of embed_edge_kernel (floats)
+constexpr int SM_P = 0;                           // [TI][EHP]
+constexpr int SM_Q = SM_P + TI * EHP;             // [TJ][QS]
+constexpr int SM_WD = SM_Q + TJ * QS;             // [EHP]
+constexpr int SM_H = ((SM_WD + EHP + 3) / 4) * 4; // [2][KC][TP][2]   h value duplicated -> packed FFMA2 operand
+constexpr int SM_W = SM_H + 2 * KC * TP * 2;      // [2][KC][EM]
+constexpr int SM_MSUM = SM_W + 2 * KC * EM;       // [TI][EM]
+constexpr int SM_GP = SM_MSUM + TI * EM;          // [4][TP] gate partial dots
+constexpr int SM_D2 = SM_GP + 4 * TP;             // [TP]
+constexpr int SM_VALID = SM_D2 + TP;              // [TP]
+constexpr int SM_B2 = SM_VALID + TP;              // [EM]
+constexpr int SM_WG = SM_B2 + EM;                 // [EM]
+constexpr int SM_FLOATS = SM_WG + EM;
+constexpr int EDGE_SMEM = SM_FLOATS * 4;
+static_assert(SM_H % 4 == 0 && SM_W % 4 == 0 && SM_P % 4 == 0, "16-byte alignment of the vector-accessed regions");
+
+__device__ __forceinline__ float silu(float x) { return __fdividef(x, 1.f + __expf(-x)); }
+__device__ __forceinline__ float sigmoidf(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+
+// acc.xy += a.xy * b.xy  (SASS FFMA2: two fp32 FMAs per issue slot)
+__device__ __forceinline__ void fma2(unsigned long long& acc, unsigned long long a, unsigned long long b) {
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
+}
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    const uint32_t d = uint32_t(__cvta_generic_to_shared(smem_dst));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------------ K_e0
+// f = pe[:L] for every structure (PositionalEncoder.forward ignores the values of its input).
+__global__ void __launch_bounds__(256) embed_init_feats_kernel(const float* __restrict__ pe, const int* __restrict__ s_start,
+                                                               const int* __restrict__ s_len, float* __restrict__ feats) {
+    const int s = blockIdx.x;
+    const int start = s_start[s], L = s_len[s];
+    const float4* src = reinterpret_cast<const float4*>(pe);
+    float4* dst = reinterpret_cast<float4*>(feats + size_t(start) * EW);
+    for (int e = threadIdx.x; e < L * (EW / 4); e += blockDim.x) dst[e] = src[e];
+}
+
+// ------------------------------------------------------------------------------------------------ K_e1
+// out[r][c] = bias[c] + sum_k f[r][k] * wt[k][c]   for 16 residues per CTA; c < ncols (thread per column).
+// Used for P|Q (wt = [128][1056]: W1a^T | W1b^T, split into two [R][528] outputs) -- FLOPs are ~0.1 % of K_e2.
+constexpr int NP_ROWS = 16;
+__global__ void __launch_bounds__(256) embed_node_proj_kernel(const float* __restrict__ feats, int n_res,
+                                                              const float* __restrict__ wt, const float* __restrict__ bias,
+                                                              float* __restrict__ outP, float* __restrict__ outQ) {
+    __shared__ float sF[NP_ROWS][EW];
+    const int r0 = blockIdx.x * NP_ROWS;
+    for (int e = threadIdx.x; e < NP_ROWS * EW; e += blockDim.x) {
+        const int r = e / EW, k = e % EW;
+        sF[r][k] = (r0 + r < n_res) ? feats[size_t(r0 + r) * EW + k] : 0.f;
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < 2 * EHP; c += blockDim.x) {
+        float acc[NP_ROWS];
+        const float b = bias[c];
+#pragma unroll
+        for (int r = 0; r < NP_ROWS; ++r) acc[r] = b;
+#pragma unroll 4
+        for (int k = 0; k < EW; ++k) {
+            const float w = wt[size_t(k) * (2 * EHP) + c];
+#pragma unroll
+            for (int r = 0; r < NP_ROWS; ++r) acc[r] = fmaf(sF[r][k], w, acc[r]);
+        }
+        float* out = (c < EHP) ? outP : outQ;
+        const int cc = (c < EHP) ? c : c - EHP;
+#pragma unroll
+        for (int r = 0; r < NP_ROWS; ++r)
+            if (r0 + r < n_res) out[size_t(r0 + r) * EHP + cc] = acc[r];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ K_e2
+struct EdgeParams {
+    const float* coords;   // [R][3]
+    const int* s_start;    // [n] first residue row of structure s
+    const int* s_len;      // [n]
+    const int2* items;     // [n_items] (structure, first residue i of the CTA), longest structures first
+    const float* P;        // [R][EHP]  W1[:, :128] f_i + b1
+    const float* Q;        // [R][EHP]  W1[:, 128:256] f_j
+    const float* wd;       // [EHP]     W1[:, 256] (the dist^2 column), zero padded
+    const float* w2t;      // [EHP][EM] W2 transposed, zero rows beyond 514
+    const float* b2;       // [EM]
+    const float* wg;       // [EM]
+    float bg;
+    float* M;              // [R][EM]   m_i = sum_j gate_ij * m_ij
+};
+
+// One CTA = TI residues i of one structure against ALL residues j of that structure, TJ at a time.
+// Tile = 128 (i,j) pairs x 256 message channels; the 514-wide hidden layer is streamed in 33 chunks of 16:
+// every chunk, the CTA (a) prefetches the next 16 rows of W2^T with cp.async, (b) generates the next
+// 16 x 128 hidden activations h = SiLU(P_i + Q_j + d2 * w_d) into shared memory (each stored twice, so that an
+// LDS.64 yields the {h,h} operand of a packed FMA), (c) runs 16 x 32 FFMA2 per thread on the current chunk.
+__global__ void __launch_bounds__(EDGE_THREADS, 1) embed_edge_kernel(const EdgeParams p) {
+    extern __shared__ __align__(16) float sm[];
+    float* sP = sm + SM_P;
+    float* sQ = sm + SM_Q;
+    float* sWd = sm + SM_WD;
+    float* sH = sm + SM_H;
+    float* sW = sm + SM_W;
+    float* sMsum = sm + SM_MSUM;
+    float* sGp = sm + SM_GP;
+    float* sD2 = sm + SM_D2;
+    float* sValid = sm + SM_VALID;
+    float* sB2 = sm + SM_B2;
+    float* sWg = sm + SM_WG;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int2 item = p.items[blockIdx.x];
+    const int start = p.s_start[item.x], L = p.s_len[item.x], i0 = item.y;
+
+    // FMA-phase coordinates: warp = (pair block, channel block); lane = (lp: 4 pair quads, lc: 8 channel quads)
+    const int warp_p = warp & 3, warp_c = warp >> 2;
+    const int lc = lane & 7, lp = lane >> 3;
+    // generation-phase coordinates: one pair, four hidden units per chunk
+    const int g_pair = tid & (TP - 1), g_kq = tid >> 7;
+    const int g_il = g_pair >> 4, g_jl = g_pair & (TJ - 1);
+
+    // ---- per-CTA setup: P rows of the TI residues (clamped inside the structure), constants, zeroed sums
+    for (int e = tid; e < TI * (EHP / 4); e += EDGE_THREADS) {
+        const int r = e / (EHP / 4), c4 = e % (EHP / 4);
+        const int row = start + min(i0 + r, L - 1);
+        reinterpret_cast<float4*>(sP)[r * (EHP / 4) + c4] = reinterpret_cast<const float4*>(p.P + size_t(row) * EHP)[c4];
+    }
+    for (int e = tid; e < EHP; e += EDGE_THREADS) sWd[e] = p.wd[e];
+    for (int e = tid; e < EM; e += EDGE_THREADS) {
+        sB2[e] = p.b2[e];
+        sWg[e] = p.wg[e];
+    }
+    for (int e = tid; e < TI * EM; e += EDGE_THREADS) sMsum[e] = 0.f;
+
+    auto load_w_chunk = [&](int kc, int buf) {  // 16 rows of W2^T = 16 KB contiguous
+        const float* src = p.w2t + size_t(kc) * KC * EM;
+        float* dst = sW + buf * (KC * EM);
+#pragma unroll
+        for (int u = 0; u < (KC * EM / 4) / EDGE_THREADS; ++u) {
+            const int e = tid + u * EDGE_THREADS;
+            cp_async16(dst + e * 4, src + e * 4);
+        }
+    };
+    auto gen_h_chunk = [&](int kc, int buf, float d2) {
+        float2* dst = reinterpret_cast<float2*>(sH + buf * (KC * TP * 2));
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int kl = g_kq * 4 + u, kg = kc * KC + kl;
+            const float x = fmaf(d2, sWd[kg], sP[g_il * EHP + kg] + sQ[g_jl * QS + kg]);
+            const float h = silu(x);
+            dst[kl * TP + g_pair] = make_float2(h, h);
+        }
+    };
+
+    for (int j0 = 0; j0 < L; j0 += TJ) {
+        // ---- tile setup: Q rows of the TJ residues j, squared distances, validity
+        for (int e = tid; e < TJ * (EHP / 4); e += EDGE_THREADS) {
+            const int r = e / (EHP / 4), c4 = e % (EHP / 4);
+            const int row = start + min(j0 + r, L - 1);
+            const float4 v = reinterpret_cast<const float4*>(p.Q + size_t(row) * EHP)[c4];
+            float* d = sQ + r * QS + c4 * 4;
+            d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+        }
+        if (tid < TP) {
+            const int il = tid >> 4, jl = tid & (TJ - 1);
+            const int ri = start + min(i0 + il, L - 1), rj = start + min(j0 + jl, L - 1);
+            const float dx = p.coords[size_t(ri) * 3 + 0] - p.coords[size_t(rj) * 3 + 0];
+            const float dy = p.coords[size_t(ri) * 3 + 1] - p.coords[size_t(rj) * 3 + 1];
+            const float dz = p.coords[size_t(ri) * 3 + 2] - p.coords[size_t(rj) * 3 + 2];
+            const float dist = sqrtf(dx * dx + dy * dy + dz * dz);  // torch.linalg.norm, my_egnn_nocoords.py:49
+            sD2[tid] = dist * dist;                                 // edge_input takes dist*dist, :58
+            sValid[tid] = (i0 + il < L && j0 + jl < L) ? 1.f : 0.f;
+        }
+        __syncthreads();
+        const float g_d2 = sD2[g_pair];
+        load_w_chunk(0, 0);
+        gen_h_chunk(0, 0, g_d2);
+        cp_async_wait_all();
+        __syncthreads();
+
+        unsigned long long acc[8][4];  // [pair pp][channel pair cc] packed {even, odd} channel
+#pragma unroll
+        for (int pp = 0; pp < 8; ++pp)
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) acc[pp][cc] = 0ull;
+
+#pragma unroll 1
+        for (int kc = 0; kc < NCHUNK; ++kc) {
+            const int cur = kc & 1;
+            if (kc + 1 < NCHUNK) {
+                load_w_chunk(kc + 1, cur ^ 1);
+                gen_h_chunk(kc + 1, cur ^ 1, g_d2);
+            }
+            const float* hb = sH + cur * (KC * TP * 2) + (warp_p * 32 + lp * 4) * 2;
+            const float* wb = sW + cur * (KC * EM) + warp_c * 64 + lc * 4;
+#pragma unroll
+            for (int kl = 0; kl < KC; ++kl) {
+                // 8 pairs: two groups of four consecutive pairs (i_local = 2*warp_p + group), duplicated values
+                const ulonglong2 h0 = *reinterpret_cast<const ulonglong2*>(hb + kl * (TP * 2));
+                const ulonglong2 h1 = *reinterpret_cast<const ulonglong2*>(hb + kl * (TP * 2) + 4);
+                const ulonglong2 h2 = *reinterpret_cast<const ulonglong2*>(hb + kl * (TP * 2) + 32);
+                const ulonglong2 h3 = *reinterpret_cast<const ulonglong2*>(hb + kl * (TP * 2) + 36);
+                // 8 channels: warp_c*64 + lc*4 + {0..3} and + 32
+                const ulonglong2 w0 = *reinterpret_cast<const ulonglong2*>(wb + kl * EM);
+                const ulonglong2 w1 = *reinterpret_cast<const ulonglong2*>(wb + kl * EM + 32);
+                const unsigned long long hv[8] = {h0.x, h0.y, h1.x, h1.y, h2.x, h2.y, h3.x, h3.y};
+                const unsigned long long wv[4] = {w0.x, w0.y, w1.x, w1.y};
+#pragma unroll
+                for (int pp = 0; pp < 8; ++pp)
+#pragma unroll
+                    for (int cc = 0; cc < 4; ++cc) fma2(acc[pp][cc], hv[pp], wv[cc]);
+            }
+            cp_async_wait_all();
+            __syncthreads();
+        }
+
+        // ---- tile epilogue: m = SiLU(acc + b2); gate = sigmoid(wg . m + bg); m_i += gate * m
+        float gd[8];
+#pragma unroll
+        for (int pp = 0; pp < 8; ++pp) gd[pp] = 0.f;
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+            const int c = warp_c * 64 + (cc >> 1) * 32 + lc * 4 + (cc & 1) * 2;
+            const float b0 = sB2[c], b1 = sB2[c + 1], g0 = sWg[c], g1 = sWg[c + 1];
+#pragma unroll
+            for (int pp = 0; pp < 8; ++pp) {
+                float2 v = *reinterpret_cast<float2*>(&acc[pp][cc]);
+                v.x = silu(v.x + b0);
+                v.y = silu(v.y + b1);
+                gd[pp] = fmaf(v.y, g1, fmaf(v.x, g0, gd[pp]));
+                acc[pp][cc] = *reinterpret_cast<unsigned long long*>(&v);
+            }
+        }
+#pragma unroll
+        for (int pp = 0; pp < 8; ++pp) {  // sum over the 8 lanes (lc) that share these pairs: this warp's 64 channels
+            gd[pp] += __shfl_xor_sync(0xffffffffu, gd[pp], 1);
+            gd[pp] += __shfl_xor_sync(0xffffffffu, gd[pp], 2);
+            gd[pp] += __shfl_xor_sync(0xffffffffu, gd[pp], 4);
+        }
+        if (lc == 0) {
+#pragma unroll
+            for (int pp = 0; pp < 8; ++pp) sGp[warp_c * TP + warp_p * 32 + (pp >> 2) * 16 + lp * 4 + (pp & 3)] = gd[pp];
+        }
+        __syncthreads();
+        float ms[2][8];
+#pragma unroll
+        for (int g = 0; g < 2; ++g)
+#pragma unroll
+            for (int c = 0; c < 8; ++c) ms[g][c] = 0.f;
+#pragma unroll
+        for (int pp = 0; pp < 8; ++pp) {
+            const int pl = warp_p * 32 + (pp >> 2) * 16 + lp * 4 + (pp & 3);
+            const float dot = ((sGp[pl] + sGp[TP + pl]) + (sGp[2 * TP + pl] + sGp[3 * TP + pl])) + p.bg;
+            const float gate = sigmoidf(dot) * sValid[pl];
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+                const float2 v = *reinterpret_cast<const float2*>(&acc[pp][cc]);
+                ms[pp >> 2][cc * 2 + 0] = fmaf(gate, v.x, ms[pp >> 2][cc * 2 + 0]);
+                ms[pp >> 2][cc * 2 + 1] = fmaf(gate, v.y, ms[pp >> 2][cc * 2 + 1]);
+            }
+        }
+#pragma unroll
+        for (int g = 0; g < 2; ++g)
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {  // sum over the 4 lane groups (lp) that hold the other j of this tile
+                ms[g][c] += __shfl_xor_sync(0xffffffffu, ms[g][c], 8);
+                ms[g][c] += __shfl_xor_sync(0xffffffffu, ms[g][c], 16);
+            }
+        if (lp == 0) {  // (i_local, channel) is owned by exactly one thread of the CTA: plain read-modify-write
+#pragma unroll
+            for (int g = 0; g < 2; ++g)
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc) {
+                    const int c = warp_c * 64 + (cc >> 1) * 32 + lc * 4 + (cc & 1) * 2;
+                    float* d = sMsum + (warp_p * 2 + g) * EM + c;
+                    d[0] += ms[g][cc * 2 + 0];
+                    d[1] += ms[g][cc * 2 + 1];
+                }
+        }
+        __syncthreads();  // sValid / sD2 / sQ / sGp are rewritten by the next tile
+    }
+
+    for (int e = tid; e < TI * EM; e += EDGE_THREADS) {
+        const int il = e / EM, c = e % EM;
+        if (i0 + il < L) p.M[size_t(start + i0 + il) * EM + c] = sMsum[e];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ K_e3
+// f'[r] = W4 SiLU(W3 [f_r, m_r] + b3) + b4 + f_r      (node_mlp + residual, my_egnn_nocoords.py:71-72)
+constexpr int NM_ROWS = 16;
+__global__ void __launch_bounds__(256) embed_node_mlp_kernel(const float* __restrict__ feats, const float* __restrict__ M, int n_res,
+                                                             const float* __restrict__ w3t /*[384][256]*/, const float* __restrict__ b3,
+                                                             const float* __restrict__ w4t /*[256][128]*/, const float* __restrict__ b4,
+                                                             float* __restrict__ feats_out) {
+    __shared__ float sIn[NM_ROWS][EW + EM];
+    __shared__ float sN1[NM_ROWS][EM];
+    const int r0 = blockIdx.x * NM_ROWS, tid = threadIdx.x;
+    for (int e = tid; e < NM_ROWS * (EW + EM); e += 256) {
+        const int r = e / (EW + EM), k = e % (EW + EM);
+        float v = 0.f;
+        if (r0 + r < n_res) v = (k < EW) ? feats[size_t(r0 + r) * EW + k] : M[size_t(r0 + r) * EM + (k - EW)];
+        sIn[r][k] = v;
+    }
+    __syncthreads();
+    {
+        const int c = tid;  // 256 hidden units
+        float acc[NM_ROWS];
+        const float b = b3[c];
+#pragma unroll
+        for (int r = 0; r < NM_ROWS; ++r) acc[r] = b;
+#pragma unroll 4
+        for (int k = 0; k < EW + EM; ++k) {
+            const float w = w3t[size_t(k) * EM + c];
+#pragma unroll
+            for (int r = 0; r < NM_ROWS; ++r) acc[r] = fmaf(sIn[r][k], w, acc[r]);
+        }
+#pragma unroll
+        for (int r = 0; r < NM_ROWS; ++r) sN1[r][c] = silu(acc[r]);
+    }
+    __syncthreads();
+    {
+        const int c = tid & (EW - 1), half = tid >> 7;  // 128 outputs x 2 halves of 8 residues
+        float acc[NM_ROWS / 2];
+        const float b = b4[c];
+#pragma unroll
+        for (int r = 0; r < NM_ROWS / 2; ++r) acc[r] = b;
+#pragma unroll 4
+        for (int k = 0; k < EM; ++k) {
+            const float w = w4t[size_t(k) * EW + c];
+#pragma unroll
+            for (int r = 0; r < NM_ROWS / 2; ++r) acc[r] = fmaf(sN1[half * (NM_ROWS / 2) + r][k], w, acc[r]);
+        }
+#pragma unroll
+        for (int r = 0; r < NM_ROWS / 2; ++r) {
+            const int rr = half * (NM_ROWS / 2) + r;
+            if (r0 + rr < n_res) feats_out[size_t(r0 + rr) * EW + c] = acc[r] + sIn[rr][c];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ K_e4
+// embed = out_feats.mean(dim=1)   (nndef_fold_egnn_embed.py:61); one CTA per structure, 4 row groups x 128 columns
+__global__ void __launch_bounds__(512) embed_mean_kernel(const float* __restrict__ feats, const int* __restrict__ s_start,
+                                                         const int* __restrict__ s_len, float* __restrict__ out) {
+    __shared__ float part[4][EW];
+    const int s = blockIdx.x, c = threadIdx.x & (EW - 1), g = threadIdx.x >> 7;
+    const int start = s_start[s], L = s_len[s];
+    float acc = 0.f;
+    for (int r = g; r < L; r += 4) acc += feats[size_t(start + r) * EW + c];
+    part[g][c] = acc;
+    __syncthreads();
+    if (g == 0) out[size_t(s) * EW + c] = ((part[0][c] + part[1][c]) + (part[2][c] + part[3][c])) / float(L);
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+struct LayerDev {
+    float* w1abt = nullptr;  // [128][1056]  W1[:, :128]^T | W1[:, 128:256]^T, hidden padded to 528
+    float* b1ab = nullptr;   // [1056]       b1 | 0
+    float* wd = nullptr;     // [528]
+    float* w2t = nullptr;    // [528][256]
+    float* b2 = nullptr;     // [256]
+    float* wg = nullptr;     // [256]
+    float bg = 0.f;
+    float* w3t = nullptr;    // [384][256]
+    float* b3 = nullptr;     // [256]
+    float* w4t = nullptr;    // [256][128]
+    float* b4 = nullptr;     // [128]
+};
+
+}  // namespace
+}  // namespace fcs
+
+using namespace fcs;
+
+struct fcs_embedder {
+    int device = 0;
+    int sm_count = 0;
+    int n_layers = 0;
+    int max_len = 0;
+    LayerDev layers[4];
+    float* pe = nullptr;
+    cudaStream_t stream = nullptr;
+    static constexpr int MAX_EDGE_EVENTS = 64;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, edge_ev[2 * MAX_EDGE_EVENTS] = {};
+    // workspace (grown on demand)
+    int64_t res_cap = 0;
+    int struct_cap = 0;
+    int64_t item_cap = 0;
+    float *coords = nullptr, *feats_a = nullptr, *feats_b = nullptr, *P = nullptr, *Q = nullptr, *M = nullptr, *out = nullptr;
+    int *s_start = nullptr, *s_len = nullptr;
+    int2* items = nullptr;
+    fcs_embed_timing timing = {};
+};
+
+namespace {
+
+int efail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    fcs::set_last_error(buf);
+    return code;
+}
+#define EMB_CUDA(call)                                                                                           \
+    do {                                                                                                         \
+        cudaError_t e__ = (call);                                                                                \
+        if (e__ != cudaSuccess) {                                                                                \
+            (void)cudaGetLastError();                                                                            \
+            return efail(e__ == cudaErrorMemoryAllocation ? FCS_ERR_NOMEM : FCS_ERR_CUDA, "%s failed: %s (%s:%d)", #call, \
+                         cudaGetErrorString(e__), __FILE__, __LINE__);                                           \
+        }                                                                                                        \
+    } while (0)
+
+struct DevGuard {
+    int prev = -1;
+    bool ok;
+    explicit DevGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        ok = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DevGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+constexpr int64_t CHUNK_RESIDUES = 1 << 20;  // residues per pass: bounds the workspace at ~6.4 KB x 2^20 = 6.7 GB
+
+int upload(float** dst, const std::vector<float>& host) {
+    EMB_CUDA(cudaMalloc(dst, host.size() * sizeof(float)));
+    EMB_CUDA(cudaMemcpy(*dst, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice));
+    return FCS_OK;
+}
+
+int upload_layer(LayerDev& d, const fcs_egnn_weights& w) {
+    const int IN1 = 2 * EW + 1;  // 257
+    std::vector<float> w1abt(size_t(EW) * 2 * EHP, 0.f), b1ab(2 * EHP, 0.f), wd(EHP, 0.f), w2t(size_t(EHP) * EM, 0.f);
+    for (int c = 0; c < EH; ++c) {
+        for (int k = 0; k < EW; ++k) {
+            w1abt[size_t(k) * 2 * EHP + c] = w.edge_w1[size_t(c) * IN1 + k];
+            w1abt[size_t(k) * 2 * EHP + EHP + c] = w.edge_w1[size_t(c) * IN1 + EW + k];
+        }
+        b1ab[c] = w.edge_b1[c];
+        wd[c] = w.edge_w1[size_t(c) * IN1 + 2 * EW];
+        for (int m = 0; m < EM; ++m) w2t[size_t(c) * EM + m] = w.edge_w2[size_t(m) * EH + c];
+    }
+    std::vector<float> b2(w.edge_b2, w.edge_b2 + EM), wg(w.gate_w, w.gate_w + EM);
+    std::vector<float> w3t(size_t(EW + EM) * EM), b3(w.node_b1, w.node_b1 + EM), w4t(size_t(EM) * EW), b4(w.node_b2, w.node_b2 + EW);
+    for (int c = 0; c < EM; ++c)
+        for (int k = 0; k < EW + EM; ++k) w3t[size_t(k) * EM + c] = w.node_w1[size_t(c) * (EW + EM) + k];
+    for (int c = 0; c < EW; ++c)
+        for (int k = 0; k < EM; ++k) w4t[size_t(k) * EW + c] = w.node_w2[size_t(c) * EM + k];
+    d.bg = w.gate_b[0];
+    int rc;
+    if ((rc = upload(&d.w1abt, w1abt)) || (rc = upload(&d.b1ab, b1ab)) || (rc = upload(&d.wd, wd)) || (rc = upload(&d.w2t, w2t)) ||
+        (rc = upload(&d.b2, b2)) || (rc = upload(&d.wg, wg)) || (rc = upload(&d.w3t, w3t)) || (rc = upload(&d.b3, b3)) ||
+        (rc = upload(&d.w4t, w4t)) || (rc = upload(&d.b4, b4)))
+        return rc;
+    return FCS_OK;
+}
+
+void free_workspace(fcs_embedder* e) {
+    cudaFree(e->coords); cudaFree(e->feats_a); cudaFree(e->feats_b); cudaFree(e->P); cudaFree(e->Q); cudaFree(e->M);
+    cudaFree(e->out); cudaFree(e->s_start); cudaFree(e->s_len); cudaFree(e->items);
+    e->coords = e->feats_a = e->feats_b = e->P = e->Q = e->M = e->out = nullptr;
+    e->s_start = e->s_len = nullptr;
+    e->items = nullptr;
+    e->res_cap = 0; e->struct_cap = 0; e->item_cap = 0;
+    (void)cudaGetLastError();
+}
+
+int ensure_workspace(fcs_embedder* e, int64_t n_res, int n_structs, int64_t n_items) {
+    if (n_res <= e->res_cap && n_structs <= e->struct_cap && n_items <= e->item_cap) return FCS_OK;
+    const int64_t rc_ = std::max(n_res, e->res_cap);
+    const int sc_ = std::max(n_structs, e->struct_cap);
+    const int64_t ic_ = std::max(n_items, e->item_cap);
+    free_workspace(e);
+    EMB_CUDA(cudaMalloc(&e->coords, size_t(rc_) * 3 * 4));
+    EMB_CUDA(cudaMalloc(&e->feats_a, size_t(rc_) * EW * 4));
+    EMB_CUDA(cudaMalloc(&e->feats_b, size_t(rc_) * EW * 4));
+    EMB_CUDA(cudaMalloc(&e->P, size_t(rc_) * EHP * 4));
+    EMB_CUDA(cudaMalloc(&e->Q, size_t(rc_) * EHP * 4));
+    EMB_CUDA(cudaMalloc(&e->M, size_t(rc_) * EM * 4));
+    EMB_CUDA(cudaMalloc(&e->out, size_t(sc_) * EW * 4));
+    EMB_CUDA(cudaMalloc(&e->s_start, size_t(sc_) * 4));
+    EMB_CUDA(cudaMalloc(&e->s_len, size_t(sc_) * 4));
+    EMB_CUDA(cudaMalloc(&e->items, size_t(ic_) * sizeof(int2)));
+    e->res_cap = rc_; e->struct_cap = sc_; e->item_cap = ic_;
+    return FCS_OK;
+}
+
+// One pass over structures [s0, s1), enqueued on e->stream and synchronised before returning.  The [s1-s0,128] block
+// of embeddings goes to `out_dev`, or to the embedder's own buffer e->out when `out_dev` is null and want_out is set.
+// If dbg_layer >= 0 the pass stops after that layer (*dbg_feats = that layer's node features, e->M = its messages).
+int run_pass(fcs_embedder* e, const float* coords, const int64_t* offsets, int s0, int s1, float* out_dev, bool want_out,
+             int* edge_events, int dbg_layer = -1, const float** dbg_feats = nullptr) {
+    const int n = s1 - s0;
+    const int64_t r_base = offsets[s0], n_res = offsets[s1] - r_base;
+    std::vector<int> start(n), len(n), order(n);
+    int64_t n_items = 0;
+    for (int s = 0; s < n; ++s) {
+        start[s] = int(offsets[s0 + s] - r_base);
+        len[s] = int(offsets[s0 + s + 1] - offsets[s0 + s]);
+        n_items += (len[s] + TI - 1) / TI;
+    }
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return len[a] > len[b]; });  // longest CTAs first
+    std::vector<int2> items;
+    items.reserve(size_t(n_items));
+    for (int s : order)
+        for (int i0 = 0; i0 < len[s]; i0 += TI) items.push_back(make_int2(s, i0));
+    int rc = ensure_workspace(e, n_res, n, n_items);
+    if (rc != FCS_OK) return rc;
+    float* dst = out_dev ? out_dev : (want_out ? e->out : nullptr);
+    cudaStream_t st = e->stream;
+    // pageable sources: cudaMemcpyAsync returns once they are staged; the stream is synchronised below anyway
+    EMB_CUDA(cudaMemcpyAsync(e->coords, coords + r_base * 3, size_t(n_res) * 12, cudaMemcpyHostToDevice, st));
+    EMB_CUDA(cudaMemcpyAsync(e->s_start, start.data(), size_t(n) * 4, cudaMemcpyHostToDevice, st));
+    EMB_CUDA(cudaMemcpyAsync(e->s_len, len.data(), size_t(n) * 4, cudaMemcpyHostToDevice, st));
+    EMB_CUDA(cudaMemcpyAsync(e->items, items.data(), items.size() * sizeof(int2), cudaMemcpyHostToDevice, st));
+
+    embed_init_feats_kernel<<<n, 256, 0, st>>>(e->pe, e->s_start, e->s_len, e->feats_a);
+    EMB_CUDA(cudaGetLastError());
+    ++e->timing.last_launches;
+    float* fin = e->feats_a;
+    float* fout = e->feats_b;
+    const int row_blocks = int((n_res + NP_ROWS - 1) / NP_ROWS);
+    for (int l = 0; l < e->n_layers; ++l) {
+        const LayerDev& w = e->layers[l];
+        embed_node_proj_kernel<<<row_blocks, 256, 0, st>>>(fin, int(n_res), w.w1abt, w.b1ab, e->P, e->Q);
+        EMB_CUDA(cudaGetLastError());
+        EdgeParams ep;
+        ep.coords = e->coords; ep.s_start = e->s_start; ep.s_len = e->s_len; ep.items = e->items;
+        ep.P = e->P; ep.Q = e->Q; ep.wd = w.wd; ep.w2t = w.w2t; ep.b2 = w.b2; ep.wg = w.wg; ep.bg = w.bg; ep.M = e->M;
+        const bool timed = *edge_events < fcs_embedder::MAX_EDGE_EVENTS;
+        if (timed) EMB_CUDA(cudaEventRecord(e->edge_ev[2 * *edge_events], st));
+        embed_edge_kernel<<<int(n_items), EDGE_THREADS, EDGE_SMEM, st>>>(ep);
+        EMB_CUDA(cudaGetLastError());
+        if (timed) {
+            EMB_CUDA(cudaEventRecord(e->edge_ev[2 * *edge_events + 1], st));
+            ++*edge_events;
+        }
+        embed_node_mlp_kernel<<<(int(n_res) + NM_ROWS - 1) / NM_ROWS, 256, 0, st>>>(fin, e->M, int(n_res), w.w3t, w.b3, w.w4t, w.b4, fout);
+        EMB_CUDA(cudaGetLastError());
+        e->timing.last_launches += 3;
+        std::swap(fin, fout);
+        if (l == dbg_layer) {
+            *dbg_feats = fin;
+            EMB_CUDA(cudaStreamSynchronize(st));
+            return FCS_OK;
+        }
+    }
+    if (dst) {
+        embed_mean_kernel<<<n, 512, 0, st>>>(fin, e->s_start, e->s_len, dst);
+        EMB_CUDA(cudaGetLastError());
+        ++e->timing.last_launches;
+    }
+    // the next pass reuses the workspace, and the pageable staging vectors die with this frame
+    EMB_CUDA(cudaStreamSynchronize(st));
+    return FCS_OK;
+}
+
+int validate(const fcs_embedder* e, const float* coords, const int64_t* offsets, int n, const void* out) {
+    if (!e) return efail(FCS_ERR_INVALID, "fcs_embed: null embedder");
+    if (n < 0 || (n > 0 && (!coords || !offsets || !out))) return efail(FCS_ERR_INVALID, "fcs_embed: null argument");
+    for (int s = 0; s < n; ++s) {
+        const int64_t L = offsets[s + 1] - offsets[s];
+        if (L < 1 || L > e->max_len)
+            return efail(FCS_ERR_INVALID, "fcs_embed: structure %d has %lld residues; 1..%d supported (positional table, "
+                         "nndef_fold_egnn_embed.py:13)", s, (long long)L, e->max_len);
+    }
+    if (n > 0 && offsets[0] < 0) return efail(FCS_ERR_INVALID, "fcs_embed: negative offset");
+    return FCS_OK;
+}
+
+// out_dev == nullptr: results go to out_host through e->out
+int embed_impl(fcs_embedder* e, const float* coords, const int64_t* offsets, int n, float* out_host, float* out_dev) {
+    int rc = validate(e, coords, offsets, n, out_host ? (const void*)out_host : (const void*)out_dev);
+    if (rc != FCS_OK) return rc;
+    DevGuard guard(e->device);
+    if (!guard.ok) return efail(FCS_ERR_CUDA, "fcs_embed: cudaSetDevice(%d) failed", e->device);
+    e->timing = fcs_embed_timing{};
+    e->timing.last_structures = n;
+    if (n == 0) return FCS_OK;
+    e->timing.last_residues = offsets[n] - offsets[0];
+    for (int s = 0; s < n; ++s) {
+        const int64_t L = offsets[s + 1] - offsets[s];
+        e->timing.last_pairs += L * L;
+    }
+    EMB_CUDA(cudaEventRecord(e->ev0, e->stream));
+    int edge_events = 0;
+    for (int s0 = 0; s0 < n;) {
+        int s1 = s0 + 1;
+        while (s1 < n && offsets[s1 + 1] - offsets[s0] <= CHUNK_RESIDUES) ++s1;
+        rc = run_pass(e, coords, offsets, s0, s1, out_dev ? out_dev + size_t(s0) * EW : nullptr, true, &edge_events);
+        if (rc != FCS_OK) return rc;
+        if (!out_dev) {
+            EMB_CUDA(cudaMemcpyAsync(out_host + size_t(s0) * EW, e->out, size_t(s1 - s0) * EW * 4, cudaMemcpyDeviceToHost, e->stream));
+            EMB_CUDA(cudaStreamSynchronize(e->stream));
+        }
+        s0 = s1;
+    }
+    EMB_CUDA(cudaEventRecord(e->ev1, e->stream));
+    EMB_CUDA(cudaStreamSynchronize(e->stream));
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, e->ev0, e->ev1) == cudaSuccess) e->timing.last_ms = ms;
+    for (int i = 0; i < edge_events; ++i)
+        if (cudaEventElapsedTime(&ms, e->edge_ev[2 * i], e->edge_ev[2 * i + 1]) == cudaSuccess) e->timing.last_edge_ms += ms;
+    return FCS_OK;
+}
+
+}  // namespace
+
+extern "C" int fcs_embedder_create(int device, const fcs_egnn_weights* layers, int n_layers, const float* pe, int max_len,
+                                   fcs_embedder** out) {
+    if (!out) return efail(FCS_ERR_INVALID, "fcs_embedder_create: out is null");
+    *out = nullptr;
+    if (!layers || !pe || n_layers < 1 || n_layers > 4 || max_len < 1)
+        return efail(FCS_ERR_INVALID, "fcs_embedder_create: need 1..4 layers, a positional table and max_len >= 1");
+    for (int l = 0; l < n_layers; ++l) {
+        const fcs_egnn_weights& w = layers[l];
+        if (!w.edge_w1 || !w.edge_b1 || !w.edge_w2 || !w.edge_b2 || !w.gate_w || !w.gate_b || !w.node_w1 || !w.node_b1 ||
+            !w.node_w2 || !w.node_b2)
+            return efail(FCS_ERR_INVALID, "fcs_embedder_create: layer %d has a null weight pointer", l);
+    }
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count < 1) {
+        (void)cudaGetLastError();
+        return efail(FCS_ERR_CUDA, "fcs_embedder_create: no usable CUDA device (this library has no CPU path)");
+    }
+    if (device < 0 || device >= count) return efail(FCS_ERR_INVALID, "fcs_embedder_create: device %d out of range", device);
+    DevGuard guard(device);
+    if (!guard.ok) return efail(FCS_ERR_CUDA, "fcs_embedder_create: cudaSetDevice(%d) failed", device);
+    fcs_embedder* e = new (std::nothrow) fcs_embedder();
+    if (!e) return efail(FCS_ERR_NOMEM, "fcs_embedder_create: out of host memory");
+    e->device = device;
+    e->n_layers = n_layers;
+    e->max_len = max_len < FCS_EMBED_MAX_LEN ? max_len : FCS_EMBED_MAX_LEN;
+    auto run = [&]() -> int {
+        cudaDeviceProp prop;
+        EMB_CUDA(cudaGetDeviceProperties(&prop, device));
+        if (prop.major < 10) return efail(FCS_ERR_UNSUPPORTED, "fcs_embedder_create: built for sm_100a, device is sm_%d%d", prop.major, prop.minor);
+        e->sm_count = prop.multiProcessorCount;
+        EMB_CUDA(cudaFuncSetAttribute(embed_edge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, EDGE_SMEM));
+        EMB_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+        EMB_CUDA(cudaEventCreate(&e->ev0));
+        EMB_CUDA(cudaEventCreate(&e->ev1));
+        for (cudaEvent_t& ev : e->edge_ev) EMB_CUDA(cudaEventCreate(&ev));
+        std::vector<float> pe_h(pe, pe + size_t(e->max_len) * EW);
+        int rc = upload(&e->pe, pe_h);
+        if (rc != FCS_OK) return rc;
+        for (int l = 0; l < n_layers; ++l)
+            if ((rc = upload_layer(e->layers[l], layers[l])) != FCS_OK) return rc;
+        return FCS_OK;
+    };
+    const int rc = run();
+    if (rc != FCS_OK) {
+        fcs_embedder_destroy(e);
+        return rc;
+    }
+    *out = e;
+    return FCS_OK;
+}
+
+extern "C" int fcs_embedder_destroy(fcs_embedder* e) {
+    if (!e) return FCS_OK;
+    DevGuard guard(e->device);
+    free_workspace(e);
+    for (LayerDev& d : e->layers) {
+        cudaFree(d.w1abt); cudaFree(d.b1ab); cudaFree(d.wd); cudaFree(d.w2t); cudaFree(d.b2); cudaFree(d.wg);
+        cudaFree(d.w3t); cudaFree(d.b3); cudaFree(d.w4t); cudaFree(d.b4);
+    }
+    cudaFree(e->pe);
+    if (e->ev0) cudaEventDestroy(e->ev0);
+    if (e->ev1) cudaEventDestroy(e->ev1);
+    for (cudaEvent_t ev : e->edge_ev)
+        if (ev) cudaEventDestroy(ev);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    (void)cudaGetLastError();
+    delete e;
+    return FCS_OK;
+}
+
+extern "C" int fcs_embed(fcs_embedder* e, const float* coords, const int64_t* offsets, int n, float* out_host) {
+    return embed_impl(e, coords, offsets, n, out_host, nullptr);
+}
+
+extern "C" int fcs_embed_to_device(fcs_embedder* e, const float* coords, const int64_t* offsets, int n, float* out_dev) {
+    if (n > 0 && !out_dev) return efail(FCS_ERR_INVALID, "fcs_embed_to_device: out_dev is null");
+    return embed_impl(e, coords, offsets, n, nullptr, out_dev);
+}
+
+extern "C" int fcs_embed_get_timing(const fcs_embedder* e, fcs_embed_timing* out) {
+    if (!e || !out) return efail(FCS_ERR_INVALID, "fcs_embed_get_timing: null argument");
+    *out = e->timing;
+    return FCS_OK;
+}
+
+extern "C" int fcs_embed_debug_layer(fcs_embedder* e, const float* coords, int length, int layer, float* out_feats, float* out_messages) {
+    if (!e || !coords) return efail(FCS_ERR_INVALID, "fcs_embed_debug_layer: null argument");
+    if (layer < 0 || layer >= e->n_layers) return efail(FCS_ERR_INVALID, "fcs_embed_debug_layer: layer %d out of range", layer);
+    const int64_t offsets[2] = {0, length};
+    int rc = validate(e, coords, offsets, 1, coords);
+    if (rc != FCS_OK) return rc;
+    DevGuard guard(e->device);
+    if (!guard.ok) return efail(FCS_ERR_CUDA, "fcs_embed_debug_layer: cudaSetDevice(%d) failed", e->device);
+    e->timing = fcs_embed_timing{};
+    int edge_events = 0;
+    const float* feats = nullptr;
+    rc = run_pass(e, coords, offsets, 0, 1, nullptr, false, &edge_events, layer, &feats);
+    if (rc != FCS_OK) return rc;
+    EMB_CUDA(cudaStreamSynchronize(e->stream));
+    if (out_feats) EMB_CUDA(cudaMemcpy(out_feats, feats, size_t(length) * EW * 4, cudaMemcpyDeviceToHost));
+    if (out_messages) EMB_CUDA(cudaMemcpy(out_messages, e->M, size_t(length) * EM * 4, cudaMemcpyDeviceToHost));
+    return FCS_OK;
+}

@@ -8,6 +8,9 @@
 
 namespace fcs {
 
+// thread-local message behind fcs_last_error() (fcs_api.cu); used by the other translation units of the C ABI
+void set_last_error(const char* msg);
+
 // ------------------------------------------------------------------ GEMV path (fcs_gemv.cu)
 constexpr int GEMV_MAX_NQ = 8;     // queries scored per DB pass by one launch
 constexpr int GEMV_MAX_K = 128;    // k per launch (register-resident lists); larger k = several passes

@@ -7,7 +7,8 @@ reference's own drivers (``dbsearch``, ``run_dbsearch``, ``multi_domain_search``
   search_query_against_db(query_dict, target_dict, ...)   reference dbsearch.py:75-81
   knn_exact(xq, db_iterator, k, ...)                      reference dbsearch.py:213-248 (knn_exact_faiss)
   dbsearch_faiss(queries, target_dict, ...)               reference dbsearch.py:203-472 (see faiss_driver.py)
-  install(reference_module)                               splice the above into the reference module
+  install(reference_module)                               splice the above into the reference module (and wrap its
+                                                          network_setup so CUDA runs get the batched embedder, embed.py)
 
 The arithmetic runs in libfcsearch.so (hand-written sm_100a CUDA) on device-resident, row-sharded
 databases; there is no CPU path here -- without the library or a GPU these functions raise.
@@ -188,4 +189,10 @@ def install(reference_module=None):
     reference_module.read_database = read_database
     reference_module.search_query_against_db = search_query_against_db
     reference_module.dbsearch_faiss = faiss_driver.dbsearch_faiss
+    # the step before the search: network_setup (dbsearch.py:35-45) hands back the batched CUDA embedder on CUDA devices
+    ref_setup = getattr(reference_module, "network_setup", None)
+    if callable(ref_setup) and not hasattr(ref_setup, "__wrapped__"):
+        from .embed import wrap_network_setup
+
+        reference_module.network_setup = wrap_network_setup(ref_setup)
     return reference_module

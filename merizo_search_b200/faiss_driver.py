@@ -11,8 +11,9 @@ dbsearch.py:472 return value, Appendix B of SURVEY.md for the hit-dict keys) so 
     ``np.memmap`` reads over the same on-disk formats (dbutil.py:37-43 sketches these readers)
     instead of one ``mmap.seek/read`` per hit (dbsearch.py:342-387).
 
-Query embedding, PDB I/O and TM-align stay the reference's own code: they are imported from the
-reference package at call time (``programs.Foldclass.utils``), exactly as the reference does.
+PDB I/O and TM-align stay the reference's own code: they are imported from the reference package at call
+time (``programs.Foldclass.utils``), exactly as the reference does.  The query embedding runs as ONE batched
+CUDA forward when ``network`` is a ``merizo_search_b200.embed.FoldClassEmbedder``.
 """
 from __future__ import annotations
 
@@ -108,21 +109,28 @@ def _reference_utils():
 
 
 def embed_queries(queries, network, device, inputs_are_ca: bool, pdb_chains: List[str]):
-    """One forward pass of the reference's FoldClassNet per query (dbsearch.py:287-301); out of scope
-    for acceleration, kept serial like the reference."""
+    """Query embedding step of the reference driver (dbsearch.py:287-301).  With a ``FoldClassEmbedder`` as
+    ``network`` (what ``install()`` arranges on CUDA devices) the whole batch is embedded by one call of the
+    batched CUDA forward; any other ``network`` (the reference's torch module) is called once per query like
+    the reference does."""
     import torch
+
+    from .embed import FoldClassEmbedder
 
     ref_utils = None
     query_dicts = []
+    for i, qy in enumerate(queries):
+        if inputs_are_ca:
+            qd = qy
+        else:
+            ref_utils = ref_utils or _reference_utils()
+            qd = ref_utils.read_pdb(pdbfile=qy, pdb_chain=pdb_chains[i])
+        query_dicts.append(qd)
+    if isinstance(network, FoldClassEmbedder):
+        return query_dicts, network.embed_structures([qd["coords"] for qd in query_dicts])
     emb = np.zeros((len(queries), native.DIM), dtype=np.float32)
     with torch.no_grad():
-        for i, qy in enumerate(queries):
-            if inputs_are_ca:
-                qd = qy
-            else:
-                ref_utils = ref_utils or _reference_utils()
-                qd = ref_utils.read_pdb(pdbfile=qy, pdb_chain=pdb_chains[i])
-            query_dicts.append(qd)
+        for i, qd in enumerate(query_dicts):
             x = torch.from_numpy(qd["coords"]).unsqueeze(0).to(device)
             emb[i] = network(x).detach().to("cpu", torch.float32).numpy().reshape(-1)
     return query_dicts, emb

@@ -26,6 +26,9 @@ EXPORTS = [
     "fcs_version", "fcs_last_error", "fcs_device_count", "fcs_db_create", "fcs_db_upload",
     "fcs_db_upload_device", "fcs_db_finalize", "fcs_db_get_info", "fcs_db_destroy", "fcs_search",
     "fcs_search_device", "fcs_merge_topk", "fcs_get_timing", "fcs_set_profiling", "fcs_debug_tc_approx",
+    # include/fcsembed.h
+    "fcs_embedder_create", "fcs_embedder_destroy", "fcs_embed", "fcs_embed_to_device", "fcs_embed_get_timing",
+    "fcs_embed_debug_layer",
 ]
 
 
@@ -43,6 +46,17 @@ class Timing(C.Structure):
 class Info(C.Structure):
     _fields_ = [("n_rows", C.c_int64), ("id_offset", C.c_int64), ("device", C.c_int32), ("flags", C.c_uint32),
                 ("finalized", C.c_int32), ("sm_count", C.c_int32), ("bytes_fp32", C.c_uint64), ("bytes_bf16", C.c_uint64)]
+
+
+class EgnnWeights(C.Structure):
+    """fcs_egnn_weights: ten host pointers (fp32, nn.Linear layout), include/fcsembed.h."""
+    FIELDS = ("edge_w1", "edge_b1", "edge_w2", "edge_b2", "gate_w", "gate_b", "node_w1", "node_b1", "node_w2", "node_b2")
+    _fields_ = [(name, C.c_void_p) for name in FIELDS]
+
+
+class EmbedTiming(C.Structure):
+    _fields_ = [("last_ms", C.c_float), ("last_edge_ms", C.c_float), ("last_launches", C.c_int32),
+                ("last_structures", C.c_int32), ("last_residues", C.c_int64), ("last_pairs", C.c_int64)]
 
 
 _lib: Optional[C.CDLL] = None
@@ -82,6 +96,12 @@ def load() -> C.CDLL:
     lib.fcs_get_timing.argtypes = [vp, C.POINTER(Timing)]
     lib.fcs_debug_tc_approx.argtypes = [vp, vp, i32, i32, vp]
     lib.fcs_set_profiling.argtypes = [vp, i32]
+    lib.fcs_embedder_create.argtypes = [i32, C.POINTER(EgnnWeights), i32, vp, i32, C.POINTER(vp)]
+    lib.fcs_embedder_destroy.argtypes = [vp]
+    lib.fcs_embed.argtypes = [vp, vp, vp, i32, vp]
+    lib.fcs_embed_to_device.argtypes = [vp, vp, vp, i32, vp]
+    lib.fcs_embed_get_timing.argtypes = [vp, C.POINTER(EmbedTiming)]
+    lib.fcs_embed_debug_layer.argtypes = [vp, vp, i32, i32, vp, vp]
     for name in EXPORTS:
         if name not in ("fcs_last_error",):
             getattr(lib, name).restype = C.c_int
@@ -196,3 +216,90 @@ def merge_topk(device: int, keys_ptr: int, n_lists: int, nq: int, k: int, out_sc
                stream: int = 0) -> None:
     _check(load().fcs_merge_topk(int(device), C.c_void_p(keys_ptr), int(n_lists), int(nq), int(k),
                                  C.c_void_p(out_scores_ptr), C.c_void_p(out_ids_ptr), C.c_void_p(stream) if stream else None))
+
+
+# state_dict key suffix of every fcs_egnn_weights field (encode_ca_egnn.<layer>.<suffix>) and its shape
+EGNN_KEYS = {
+    "edge_w1": ("edge_mlp.0.weight", (514, 257)), "edge_b1": ("edge_mlp.0.bias", (514,)),
+    "edge_w2": ("edge_mlp.2.weight", (256, 514)), "edge_b2": ("edge_mlp.2.bias", (256,)),
+    "gate_w": ("edge_gate.0.weight", (1, 256)), "gate_b": ("edge_gate.0.bias", (1,)),
+    "node_w1": ("node_mlp.0.weight", (256, 384)), "node_b1": ("node_mlp.0.bias", (256,)),
+    "node_w2": ("node_mlp.2.weight", (128, 256)), "node_b2": ("node_mlp.2.bias", (128,)),
+}
+
+
+class Embedder:
+    """Device-resident FoldClassNet(128) weights + the batched forward (fcs_embedder).  Not re-entrant."""
+
+    def __init__(self, layers, pe: np.ndarray, device: int = 0):
+        """layers: list (one per EGNN layer) of dicts field name -> fp32 array (EGNN_KEYS shapes);
+        pe: the positional table [max_len, 128]."""
+        self._lib = load()
+        self._h = C.c_void_p()
+        pe = np.ascontiguousarray(pe, dtype=np.float32).reshape(-1, DIM)
+        keep = []  # the arrays must outlive the create call only (the library copies them to the device)
+        arr = (EgnnWeights * len(layers))()
+        for i, layer in enumerate(layers):
+            for name in EgnnWeights.FIELDS:
+                a = np.ascontiguousarray(layer[name], dtype=np.float32)
+                if a.shape != EGNN_KEYS[name][1]:
+                    raise FcsError(ERR_INVALID, f"layer {i}: {name} has shape {a.shape}, expected {EGNN_KEYS[name][1]}")
+                keep.append(a)
+                setattr(arr[i], name, a.ctypes.data_as(C.c_void_p))
+        _check(self._lib.fcs_embedder_create(int(device), arr, len(layers), _np_ptr(pe), int(pe.shape[0]), C.byref(self._h)))
+        self.device, self.n_layers, self.max_len = int(device), len(layers), int(pe.shape[0])
+
+    @staticmethod
+    def _pack(structures):
+        lens = [int(np.asarray(c).reshape(-1, 3).shape[0]) for c in structures]
+        offsets = np.zeros(len(lens) + 1, dtype=np.int64)
+        offsets[1:] = np.cumsum(lens)
+        if len(lens):
+            coords = np.concatenate([np.asarray(c, dtype=np.float32).reshape(-1, 3) for c in structures])
+        else:
+            coords = np.zeros((0, 3), dtype=np.float32)
+        return np.ascontiguousarray(coords, dtype=np.float32), offsets
+
+    def embed(self, structures) -> np.ndarray:
+        """list of [L,3] C-alpha traces -> host array [n,128]."""
+        coords, offsets = self._pack(structures)
+        return self.embed_packed(coords, offsets)
+
+    def embed_packed(self, coords: np.ndarray, offsets: np.ndarray) -> np.ndarray:
+        coords = np.ascontiguousarray(coords, dtype=np.float32).reshape(-1, 3)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        n = offsets.shape[0] - 1
+        out = np.empty((n, DIM), dtype=np.float32)
+        _check(self._lib.fcs_embed(self._h, _np_ptr(coords), _np_ptr(offsets), n, _np_ptr(out)))
+        return out
+
+    def embed_packed_to_device(self, coords: np.ndarray, offsets: np.ndarray, out_ptr: int) -> None:
+        """Same, the [n,128] fp32 result is written to device memory at `out_ptr` (complete on return)."""
+        coords = np.ascontiguousarray(coords, dtype=np.float32).reshape(-1, 3)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        _check(self._lib.fcs_embed_to_device(self._h, _np_ptr(coords), _np_ptr(offsets), offsets.shape[0] - 1, C.c_void_p(out_ptr)))
+
+    def debug_layer(self, coords: np.ndarray, layer: int):
+        """Test hook: (node features after `layer` [L,128], summed messages of that layer [L,256])."""
+        coords = np.ascontiguousarray(coords, dtype=np.float32).reshape(-1, 3)
+        L = coords.shape[0]
+        feats = np.empty((L, DIM), dtype=np.float32)
+        msgs = np.empty((L, 256), dtype=np.float32)
+        _check(self._lib.fcs_embed_debug_layer(self._h, _np_ptr(coords), L, int(layer), _np_ptr(feats), _np_ptr(msgs)))
+        return feats, msgs
+
+    def timing(self) -> EmbedTiming:
+        t = EmbedTiming()
+        _check(self._lib.fcs_embed_get_timing(self._h, C.byref(t)))
+        return t
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.fcs_embedder_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

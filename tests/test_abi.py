@@ -13,9 +13,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _declared():
-    text = open(os.path.join(ROOT, "include", "fcsearch.h")).read()
-    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(fcs_[a-z0-9_]+)\s*\(", text)))
+    names = set()
+    for header in ("fcsearch.h", "fcsembed.h"):
+        text = open(os.path.join(ROOT, "include", header)).read()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        names |= set(re.findall(r"\b(fcs_[a-z0-9_]+)\s*\(", text))
+    return sorted(names)
 
 
 def test_header_symbols_are_exported():
@@ -24,7 +27,7 @@ def test_header_symbols_are_exported():
     assert len(names) >= 13
     for name in names:
         assert hasattr(lib, name), f"{name} declared in fcsearch.h but not exported by libfcsearch.so"
-    assert sorted(native.EXPORTS) == names, "native.EXPORTS and include/fcsearch.h disagree"
+    assert sorted(native.EXPORTS) == names, "native.EXPORTS and include/*.h disagree"
 
 
 def test_version_and_error_string():
@@ -44,6 +47,11 @@ def test_invalid_arguments_are_codes():
     assert lib.fcs_db_finalize(None) == native.ERR_INVALID
     assert lib.fcs_search(None, None, 1, None, 0.0, 1, 0, 0, 0, None, None) == native.ERR_INVALID
     assert lib.fcs_db_destroy(None) == native.OK
+    e = C.c_void_p()
+    assert lib.fcs_embedder_create(0, None, 2, None, 3000, C.byref(e)) == native.ERR_INVALID
+    assert lib.fcs_embed(None, None, None, 1, None) == native.ERR_INVALID
+    assert b"null embedder" in lib.fcs_last_error()
+    assert lib.fcs_embedder_destroy(None) == native.OK
 
 
 def test_no_gpu_fails_loudly_not_silently():
@@ -61,3 +69,5 @@ def test_no_gpu_fails_loudly_not_silently():
 def test_struct_layouts_match_header():
     assert C.sizeof(native.Timing) == 24
     assert C.sizeof(native.Info) == 48
+    assert C.sizeof(native.EgnnWeights) == 80
+    assert C.sizeof(native.EmbedTiming) == 32
