@@ -51,3 +51,19 @@ def ip_flavour():
     db = synth.host_db(66943, base_seed=int(z["db_seed"]), normalise=True)
     assert _sha(db) == str(z["db_sha"]), "synthetic DB drifted"
     return db, z
+
+
+def embed_golden():
+    """(npz, seeded stand-in state_dict, list of [L,3] structures) of embed_foldclassnet.npz (make_golden_embed.py)."""
+    from oracle import foldclass_embed_oracle as emb
+
+    z = np.load(os.path.join(GOLDEN, "embed_foldclassnet.npz"))
+    sd = emb.synthetic_state_dict(int(z["weight_seed"]))
+    h = hashlib.sha256()
+    for key in sorted(sd):
+        h.update(key.encode())
+        h.update(np.ascontiguousarray(sd[key]).tobytes())
+    assert h.hexdigest() == str(z["weights_sha"]), "synthetic weights drifted from the ones the golden vectors were made with"
+    offsets = z["offsets"]
+    structures = [z["coords"][offsets[i]:offsets[i + 1]] for i in range(len(offsets) - 1)]
+    return z, sd, structures

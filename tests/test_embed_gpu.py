@@ -10,7 +10,7 @@ import torch
 from merizo_search_b200 import embed as b200_embed
 from merizo_search_b200 import native
 from oracle import foldclass_embed_oracle as emb
-from tests.test_embed_oracle import load_golden
+from golden_util import embed_golden as load_golden
 
 pytestmark = pytest.mark.gpu
 RTOL = 5e-5

@@ -1,7 +1,5 @@
 """CPU: the embedder's oracle (numpy restatement of FoldClassNet.forward) against golden vectors produced by
 the reference's own module (tests/golden/make_golden_embed.py), plus the host-side plumbing of the drop-in."""
-import hashlib
-import os
 import types
 
 import numpy as np
@@ -11,20 +9,7 @@ from merizo_search_b200 import embed as b200_embed
 from merizo_search_b200 import native
 from oracle import foldclass_embed_oracle as emb
 
-GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "embed_foldclassnet.npz")
-
-
-def load_golden():
-    z = np.load(GOLDEN)
-    sd = emb.synthetic_state_dict(int(z["weight_seed"]))
-    h = hashlib.sha256()
-    for key in sorted(sd):
-        h.update(key.encode())
-        h.update(np.ascontiguousarray(sd[key]).tobytes())
-    assert h.hexdigest() == str(z["weights_sha"]), "synthetic weights drifted from the ones the golden vectors were made with"
-    offsets = z["offsets"]
-    structures = [z["coords"][offsets[i]:offsets[i + 1]] for i in range(len(offsets) - 1)]
-    return z, sd, structures
+from golden_util import embed_golden as load_golden  # noqa: E402
 
 
 @pytest.mark.parametrize("factored", [False, True])
