@@ -46,18 +46,18 @@ constexpr int NCHUNK = EHP / KC;       // 33
 constexpr int TI = 8;                  // residues i per CTA
 constexpr int TJ = 16;                 // residues j per tile
 constexpr int TP = TI * TJ;            // 128 pairs per tile
-constexpr int EDGE_THREADS = 512;      // 16 warps: 4 (pair blocks of 32) x 4 (channel blocks of 64); thread = 8 pairs x 8 channels
+constexpr int EDGE_THREADS = 256;      // 8 warps: 4 (pair blocks of 32) x 2 (channel halves of 128); thread = 16 pairs x 8 channels
 constexpr int QS = EHP + 1;            // shared-memory row stride of the Q tile (conflict-free column reads)
 
 // shared-memory carve-up of embed_edge_kernel (floats)
 constexpr int SM_P = 0;                           // [TI][EHP]
 constexpr int SM_Q = SM_P + TI * EHP;             // [TJ][QS]
 constexpr int SM_WD = SM_Q + TJ * QS;             // [EHP]
-constexpr int SM_H = ((SM_WD + EHP + 3) / 4) * 4; // [2][KC][TP][2]   h value duplicated -> packed FFMA2 operand
-constexpr int SM_W = SM_H + 2 * KC * TP * 2;      // [2][KC][EM]
+constexpr int SM_H = ((SM_WD + EHP + 3) / 4) * 4; // [2][KC][TP]     hidden activations of the current / next chunk
+constexpr int SM_W = SM_H + 2 * KC * TP;          // [2][KC][EM]     rows of W2^T of the current / next chunk
 constexpr int SM_MSUM = SM_W + 2 * KC * EM;       // [TI][EM]
-constexpr int SM_GP = SM_MSUM + TI * EM;          // [4][TP] gate partial dots
-constexpr int SM_D2 = SM_GP + 4 * TP;             // [TP]
+constexpr int SM_GP = SM_MSUM + TI * EM;          // [2][TP] gate partial dots (one per channel half)
+constexpr int SM_D2 = SM_GP + 2 * TP;             // [TP]
 constexpr int SM_VALID = SM_D2 + TP;              // [TP]
 constexpr int SM_B2 = SM_VALID + TP;              // [EM]
 constexpr int SM_WG = SM_B2 + EM;                 // [EM]
@@ -71,6 +71,11 @@ __device__ __forceinline__ float sigmoidf(float x) { return __fdividef(1.f, 1.f 
 // acc.xy += a.xy * b.xy  (SASS FFMA2: two fp32 FMAs per issue slot)
 __device__ __forceinline__ void fma2(unsigned long long& acc, unsigned long long a, unsigned long long b) {
     asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
+}
+__device__ __forceinline__ unsigned long long dup2(float w) {  // {w, w}
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(r) : "r"(__float_as_uint(w)));
+    return r;
 }
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
     const uint32_t d = uint32_t(__cvta_generic_to_shared(smem_dst));
@@ -141,8 +146,12 @@ struct EdgeParams {
 // One CTA = TI residues i of one structure against ALL residues j of that structure, TJ at a time.
 // Tile = 128 (i,j) pairs x 256 message channels; the 514-wide hidden layer is streamed in 33 chunks of 16:
 // every chunk, the CTA (a) prefetches the next 16 rows of W2^T with cp.async, (b) generates the next
-// 16 x 128 hidden activations h = SiLU(P_i + Q_j + d2 * w_d) into shared memory (each stored twice, so that an
-// LDS.64 yields the {h,h} operand of a packed FMA), (c) runs 16 x 32 FFMA2 per thread on the current chunk.
+// 16 x 128 hidden activations h = SiLU(P_i + Q_j + d2 * w_d) into shared memory, (c) runs 16 x 64 FFMA2 per
+// thread on the current chunk.  A thread owns 16 pairs (ONE residue i against the tile's 16 residues j) x 8
+// channels: accumulators are packed {pair 2q, pair 2q+1} so the h operand of a packed FMA is a natural 8-byte
+// piece of an LDS.128 and only the 8 weights are duplicated in registers; 6 LDS.128 feed 64 FFMA2 (v1 of this
+// kernel had 6 per 32 and was shared-memory bound at 41 TFLOP/s).  The gate dot product needs one 16-lane
+// shuffle reduction; the sum over j is thread-local.
 __global__ void __launch_bounds__(EDGE_THREADS, 1) embed_edge_kernel(const EdgeParams p) {
     extern __shared__ __align__(16) float sm[];
     float* sP = sm + SM_P;
@@ -161,10 +170,13 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) embed_edge_kernel(const EdgeP
     const int2 item = p.items[blockIdx.x];
     const int start = p.s_start[item.x], L = p.s_len[item.x], i0 = item.y;
 
-    // FMA-phase coordinates: warp = (pair block, channel block); lane = (lp: 4 pair quads, lc: 8 channel quads)
+    // FMA-phase coordinates: warp = (pair block of 32, channel half of 128); lane = (lp: which 16 pairs, lc: channel quad)
     const int warp_p = warp & 3, warp_c = warp >> 2;
-    const int lc = lane & 7, lp = lane >> 3;
-    // generation-phase coordinates: one pair, four hidden units per chunk
+    const int lc = lane & 15, lp = lane >> 4;
+    const int my_il = warp_p * 2 + lp;           // the residue i (0..TI-1) whose 16 pairs this thread owns
+    const int my_pair0 = my_il * TJ;             // first of its 16 pairs (pair = i_local * TJ + j_local)
+    const int my_ch0 = warp_c * 128 + lc * 4;    // its channels: my_ch0 + {0..3} and my_ch0 + 64 + {0..3}
+    // generation-phase coordinates: one pair, eight hidden units per chunk
     const int g_pair = tid & (TP - 1), g_kq = tid >> 7;
     const int g_il = g_pair >> 4, g_jl = g_pair & (TJ - 1);
 
@@ -191,13 +203,12 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) embed_edge_kernel(const EdgeP
         }
     };
     auto gen_h_chunk = [&](int kc, int buf, float d2) {
-        float2* dst = reinterpret_cast<float2*>(sH + buf * (KC * TP * 2));
+        float* dst = sH + buf * (KC * TP);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int kl = g_kq * 4 + u, kg = kc * KC + kl;
+        for (int u = 0; u < KC / 2; ++u) {
+            const int kl = g_kq * (KC / 2) + u, kg = kc * KC + kl;
             const float x = fmaf(d2, sWd[kg], sP[g_il * EHP + kg] + sQ[g_jl * QS + kg]);
-            const float h = silu(x);
-            dst[kl * TP + g_pair] = make_float2(h, h);
+            dst[kl * TP + g_pair] = silu(x);
         }
     };
 
@@ -227,11 +238,11 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) embed_edge_kernel(const EdgeP
         cp_async_wait_all();
         __syncthreads();
 
-        unsigned long long acc[8][4];  // [pair pp][channel pair cc] packed {even, odd} channel
+        unsigned long long acc[8][8];  // [pair couple q = pairs 2q, 2q+1][channel c] packed {pair 2q, pair 2q+1}
 #pragma unroll
-        for (int pp = 0; pp < 8; ++pp)
+        for (int q = 0; q < 8; ++q)
 #pragma unroll
-            for (int cc = 0; cc < 4; ++cc) acc[pp][cc] = 0ull;
+            for (int c = 0; c < 8; ++c) acc[q][c] = 0ull;
 
 #pragma unroll 1
         for (int kc = 0; kc < NCHUNK; ++kc) {
@@ -240,92 +251,75 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) embed_edge_kernel(const EdgeP
                 load_w_chunk(kc + 1, cur ^ 1);
                 gen_h_chunk(kc + 1, cur ^ 1, g_d2);
             }
-            const float* hb = sH + cur * (KC * TP * 2) + (warp_p * 32 + lp * 4) * 2;
-            const float* wb = sW + cur * (KC * EM) + warp_c * 64 + lc * 4;
+            const float* hb = sH + cur * (KC * TP) + my_pair0;
+            const float* wb = sW + cur * (KC * EM) + my_ch0;
 #pragma unroll
             for (int kl = 0; kl < KC; ++kl) {
-                // 8 pairs: two groups of four consecutive pairs (i_local = 2*warp_p + group), duplicated values
-                const ulonglong2 h0 = *reinterpret_cast<const ulonglong2*>(hb + kl * (TP * 2));
-                const ulonglong2 h1 = *reinterpret_cast<const ulonglong2*>(hb + kl * (TP * 2) + 4);
-                const ulonglong2 h2 = *reinterpret_cast<const ulonglong2*>(hb + kl * (TP * 2) + 32);
-                const ulonglong2 h3 = *reinterpret_cast<const ulonglong2*>(hb + kl * (TP * 2) + 36);
-                // 8 channels: warp_c*64 + lc*4 + {0..3} and + 32
-                const ulonglong2 w0 = *reinterpret_cast<const ulonglong2*>(wb + kl * EM);
-                const ulonglong2 w1 = *reinterpret_cast<const ulonglong2*>(wb + kl * EM + 32);
+                const ulonglong2 h0 = *reinterpret_cast<const ulonglong2*>(hb + kl * TP);
+                const ulonglong2 h1 = *reinterpret_cast<const ulonglong2*>(hb + kl * TP + 4);
+                const ulonglong2 h2 = *reinterpret_cast<const ulonglong2*>(hb + kl * TP + 8);
+                const ulonglong2 h3 = *reinterpret_cast<const ulonglong2*>(hb + kl * TP + 12);
+                const float4 wa = *reinterpret_cast<const float4*>(wb + kl * EM);
+                const float4 wc = *reinterpret_cast<const float4*>(wb + kl * EM + 64);
                 const unsigned long long hv[8] = {h0.x, h0.y, h1.x, h1.y, h2.x, h2.y, h3.x, h3.y};
-                const unsigned long long wv[4] = {w0.x, w0.y, w1.x, w1.y};
+                const unsigned long long wv[8] = {dup2(wa.x), dup2(wa.y), dup2(wa.z), dup2(wa.w),
+                                                  dup2(wc.x), dup2(wc.y), dup2(wc.z), dup2(wc.w)};
 #pragma unroll
-                for (int pp = 0; pp < 8; ++pp)
+                for (int q = 0; q < 8; ++q)
 #pragma unroll
-                    for (int cc = 0; cc < 4; ++cc) fma2(acc[pp][cc], hv[pp], wv[cc]);
+                    for (int c = 0; c < 8; ++c) fma2(acc[q][c], hv[q], wv[c]);
             }
             cp_async_wait_all();
             __syncthreads();
         }
 
         // ---- tile epilogue: m = SiLU(acc + b2); gate = sigmoid(wg . m + bg); m_i += gate * m
-        float gd[8];
+        float gd[16];
 #pragma unroll
-        for (int pp = 0; pp < 8; ++pp) gd[pp] = 0.f;
+        for (int pp = 0; pp < 16; ++pp) gd[pp] = 0.f;
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-            const int c = warp_c * 64 + (cc >> 1) * 32 + lc * 4 + (cc & 1) * 2;
-            const float b0 = sB2[c], b1 = sB2[c + 1], g0 = sWg[c], g1 = sWg[c + 1];
+        for (int c = 0; c < 8; ++c) {
+            const int ch = my_ch0 + (c >> 2) * 64 + (c & 3);
+            const float b = sB2[ch], g = sWg[ch];
 #pragma unroll
-            for (int pp = 0; pp < 8; ++pp) {
-                float2 v = *reinterpret_cast<float2*>(&acc[pp][cc]);
-                v.x = silu(v.x + b0);
-                v.y = silu(v.y + b1);
-                gd[pp] = fmaf(v.y, g1, fmaf(v.x, g0, gd[pp]));
-                acc[pp][cc] = *reinterpret_cast<unsigned long long*>(&v);
+            for (int q = 0; q < 8; ++q) {
+                float2 v = *reinterpret_cast<float2*>(&acc[q][c]);
+                v.x = silu(v.x + b);
+                v.y = silu(v.y + b);
+                gd[2 * q] = fmaf(v.x, g, gd[2 * q]);
+                gd[2 * q + 1] = fmaf(v.y, g, gd[2 * q + 1]);
+                acc[q][c] = *reinterpret_cast<unsigned long long*>(&v);
             }
         }
 #pragma unroll
-        for (int pp = 0; pp < 8; ++pp) {  // sum over the 8 lanes (lc) that share these pairs: this warp's 64 channels
+        for (int pp = 0; pp < 16; ++pp) {  // sum over the 16 lanes (lc) that share these pairs: this warp's 128 channels
             gd[pp] += __shfl_xor_sync(0xffffffffu, gd[pp], 1);
             gd[pp] += __shfl_xor_sync(0xffffffffu, gd[pp], 2);
             gd[pp] += __shfl_xor_sync(0xffffffffu, gd[pp], 4);
+            gd[pp] += __shfl_xor_sync(0xffffffffu, gd[pp], 8);
         }
         if (lc == 0) {
 #pragma unroll
-            for (int pp = 0; pp < 8; ++pp) sGp[warp_c * TP + warp_p * 32 + (pp >> 2) * 16 + lp * 4 + (pp & 3)] = gd[pp];
+            for (int pp = 0; pp < 16; ++pp) sGp[warp_c * TP + my_pair0 + pp] = gd[pp];
         }
         __syncthreads();
-        float ms[2][8];
+        float ms[8];
 #pragma unroll
-        for (int g = 0; g < 2; ++g)
+        for (int c = 0; c < 8; ++c) ms[c] = 0.f;
 #pragma unroll
-            for (int c = 0; c < 8; ++c) ms[g][c] = 0.f;
+        for (int q = 0; q < 8; ++q) {
+            const int pl = my_pair0 + 2 * q;
+            const float gate0 = sigmoidf((sGp[pl] + sGp[TP + pl]) + p.bg) * sValid[pl];
+            const float gate1 = sigmoidf((sGp[pl + 1] + sGp[TP + pl + 1]) + p.bg) * sValid[pl + 1];
 #pragma unroll
-        for (int pp = 0; pp < 8; ++pp) {
-            const int pl = warp_p * 32 + (pp >> 2) * 16 + lp * 4 + (pp & 3);
-            const float dot = ((sGp[pl] + sGp[TP + pl]) + (sGp[2 * TP + pl] + sGp[3 * TP + pl])) + p.bg;
-            const float gate = sigmoidf(dot) * sValid[pl];
-#pragma unroll
-            for (int cc = 0; cc < 4; ++cc) {
-                const float2 v = *reinterpret_cast<const float2*>(&acc[pp][cc]);
-                ms[pp >> 2][cc * 2 + 0] = fmaf(gate, v.x, ms[pp >> 2][cc * 2 + 0]);
-                ms[pp >> 2][cc * 2 + 1] = fmaf(gate, v.y, ms[pp >> 2][cc * 2 + 1]);
+            for (int c = 0; c < 8; ++c) {
+                const float2 v = *reinterpret_cast<const float2*>(&acc[q][c]);
+                ms[c] = fmaf(gate1, v.y, fmaf(gate0, v.x, ms[c]));
             }
         }
+        // (i_local, channel) is owned by exactly one thread of the CTA: plain read-modify-write
 #pragma unroll
-        for (int g = 0; g < 2; ++g)
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {  // sum over the 4 lane groups (lp) that hold the other j of this tile
-                ms[g][c] += __shfl_xor_sync(0xffffffffu, ms[g][c], 8);
-                ms[g][c] += __shfl_xor_sync(0xffffffffu, ms[g][c], 16);
-            }
-        if (lp == 0) {  // (i_local, channel) is owned by exactly one thread of the CTA: plain read-modify-write
-#pragma unroll
-            for (int g = 0; g < 2; ++g)
-#pragma unroll
-                for (int cc = 0; cc < 4; ++cc) {
-                    const int c = warp_c * 64 + (cc >> 1) * 32 + lc * 4 + (cc & 1) * 2;
-                    float* d = sMsum + (warp_p * 2 + g) * EM + c;
-                    d[0] += ms[g][cc * 2 + 0];
-                    d[1] += ms[g][cc * 2 + 1];
-                }
-        }
+        for (int c = 0; c < 8; ++c) sMsum[my_il * EM + my_ch0 + (c >> 2) * 64 + (c & 3)] += ms[c];
         __syncthreads();  // sValid / sD2 / sQ / sGp are rewritten by the next tile
     }
 
