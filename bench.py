@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- queries/s of the Foldclass database search on N B200s (one rank per GPU).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2|cfg3|cfg4] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2|cfg3|cfg4|cfg4b|embed] [--impl reference]
 
 Workloads (BASELINE.json `configs`, synthetic unit-norm 128-d rows, random queries):
   cfg3 (default)  10 M rows, 4096-query batch, k=100      -- tcgen05 path; largest single-GPU config
@@ -46,6 +46,11 @@ WORKLOADS = {
                   desc="BASELINE configs[3] slice: 365M/8 = 45.625M x 128 rows per GPU, 1024-query batch, k=10, tcgen05 path"),
 }
 DEFAULT_WORKLOAD = "cfg3"
+# The step BEFORE the search: embedding the query structures.  Not a BASELINE config of its own --
+# it rides along as extra["embed"] (1 GPU) or runs alone with --workload embed.
+EMBED_WORKLOAD = dict(n=2048, len_seed=21, chain_seed=3, weight_seed=2024,
+                      desc="batched FoldClassNet(128) forward: 2048 synthetic C-alpha chains, lengths drawn like TED domains "
+                           "(25..683, mean 126), seeded stand-in weights; fused fp32 edge kernel")
 
 
 def load_peaks():
@@ -157,6 +162,87 @@ def cpu_oracle_throughput(wl, n_rows_total, budget_s=12.0):
     sample = (f"{nq_s} queries x {n} rows (of {n_rows_total}), blockwise mm+topk+merge restatement of faiss IndexFlatIP "
               f"(262144-row blocks), {dt:.2f} s/pass x {reps}, extrapolated linearly in rows")
     return qps, cores, sample
+
+
+def cpu_embed_throughput(structures, sd, budget_s=10.0):
+    """Structures/s of the CPU oracle (numpy port of FoldClassNet.forward in the reference's literal order:
+    materialised [L,L,257] edge tensor, two dense layers) on a bounded sample, all host threads via BLAS."""
+    from oracle import foldclass_embed_oracle as eorc
+
+    eorc.forward(structures[0][:32], sd, factored=False)  # warm
+    t0, done, res = time.perf_counter(), 0, 0
+    while time.perf_counter() - t0 < budget_s and done < len(structures):
+        eorc.forward(structures[done], sd, factored=False)
+        res += structures[done].shape[0]
+        done += 1
+    dt = time.perf_counter() - t0
+    return done / dt, os.cpu_count() or 1, (f"{done} structures ({res} residues) of the same batch, numpy port of the reference "
+                                            f"FoldClassNet.forward (literal order), {dt:.1f} s")
+
+
+def run_embed(args, steps=3, warmup=3, cpu_baseline=True):
+    """Embedding workload on this rank's GPU (1 GPU): structures/s of the batched CUDA forward."""
+    import torch
+
+    from merizo_search_b200 import embed as b200_embed
+    from merizo_search_b200 import native, synth
+
+    wl = EMBED_WORKLOAD
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    n = args.nq or wl["n"]
+    lens = synth.host_lengths(n, seed=wl["len_seed"])
+    structures = synth.synthetic_chains(lens, seed=wl["chain_seed"])
+    sd = synth.synthetic_state_dict(wl["weight_seed"])
+    emb = b200_embed.FoldClassEmbedder(sd, device=local_rank)
+    coords, offsets = native.Embedder._pack(structures)
+    out_dev = torch.empty((n, 128), dtype=torch.float32, device=torch.device("cuda", local_rank))
+    torch.cuda.synchronize()
+    for _ in range(max(3, warmup)):
+        emb._emb.embed_packed_to_device(coords, offsets, out_dev.data_ptr())
+    sampler = ClockSampler(local_rank)
+    dev_ms, edge_ms = [], []
+    for _ in range(steps):  # device time: CUDA events on the embedder's own stream, recorded inside the library
+        emb._emb.embed_packed_to_device(coords, offsets, out_dev.data_ptr())
+        t = emb.timing()
+        dev_ms.append(t.last_ms)
+        edge_ms.append(t.last_edge_ms)
+    clocks = sampler.stop()
+    t = emb.timing()
+    t0 = time.perf_counter()
+    for _ in range(steps):  # e2e: list of host arrays in, host matrix out (pack + H2D + kernels + D2H)
+        emb.embed_structures(structures)
+    e2e_s = (time.perf_counter() - t0) / steps
+    ms = float(np.mean(dev_ms))
+    pairs = int(t.last_pairs)
+    flops = 2.0 * 514 * 256 * pairs * 2  # edge MLP second layer, both EGNN layers: the only O(L^2 x 514 x 256) term
+    achieved = flops / (float(np.mean(edge_ms)) * 1e-3) / 1e12
+    sm_mhz = clocks.get("sm_mhz") or 1965.0
+    props = torch.cuda.get_device_properties(local_rank)
+    peak = props.multi_processor_count * 128 * 2 * sm_mhz * 1e6 / 1e12
+    out = {
+        "metric": "structures/s (FoldClassNet embedding)", "value": n / (ms * 1e-3), "unit": "structures/s", "n_gpus": 1,
+        "steps": steps, "warmup": max(3, warmup), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic (C-alpha-like random walks, seeded stand-in weights)",
+        "config": {"workload": "embed", "description": wl["desc"], "structures": n, "residues": int(t.last_residues),
+                   "pairs_per_layer": pairs, "layers": 2, "l2": "weights (0.5 MB per layer) stay in L2 by design; per-pair HBM traffic ~0"},
+        "e2e": {"value": n / e2e_s, "unit": "structures/s", "h2d_bytes_per_step": int(coords.nbytes + offsets.nbytes),
+                "d2h_bytes_per_step": int(n * 512), "ms_per_step": e2e_s * 1e3,
+                "api": "merizo_search_b200.embed.FoldClassEmbedder.embed_structures (fcs_embed: host coordinates in, host embeddings out)"},
+        "gpu_launches": int(t.last_launches) * steps,
+        "roofline": {"bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                     "kernel": "embed_edge_kernel (both layers of one batch)", "algorithmic": "2*514*256 flop per (i,j) pair per layer",
+                     "peak_source": f"derived: {props.multi_processor_count} SMs x 128 fp32 FMA lanes x 2 x {sm_mhz:.0f} MHz "
+                                    "(median SM clock sampled during the timed region); no tensor-core or HBM bound applies"},
+        "clocks": clocks,
+    }
+    if cpu_baseline:
+        v, cores, sample = cpu_embed_throughput(structures, sd, budget_s=10.0)
+        out["cpu_baseline"] = {"value": v, "unit": "structures/s", "cores": cores, "kind": "port", "sample": sample}
+    emb.close()
+    del out_dev
+    torch.cuda.empty_cache()
+    return out
 
 
 # --------------------------------------------------------------------------------------------- GPU arm
@@ -366,7 +452,7 @@ def main():
     ap.add_argument("--steps", type=int, default=0)
     ap.add_argument("--warmup", type=int, default=0)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default=os.environ.get("FCS_BENCH_WORKLOAD", DEFAULT_WORKLOAD), choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=os.environ.get("FCS_BENCH_WORKLOAD", DEFAULT_WORKLOAD), choices=sorted(WORKLOADS) + ["embed"])
     ap.add_argument("--rows", type=int, default=0, help="override the total row count (debugging)")
     ap.add_argument("--nq", type=int, default=0, help="override the batch size (debugging)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -375,6 +461,23 @@ def main():
                     help="N>1: ranks = row shards x query groups; 0 = auto (replicate the database as far as ~80 GB per "
                          "GPU allow and split the batch), 1 = pure row sharding")
     args = ap.parse_args()
+    if args.workload == "embed":  # the step before the search, alone (1 GPU)
+        if int(os.environ.get("RANK", "0")) != 0:
+            return 0
+        if args.impl == "reference":
+            from merizo_search_b200 import synth
+
+            n = args.nq or EMBED_WORKLOAD["n"]
+            structures = synth.synthetic_chains(synth.host_lengths(n, seed=EMBED_WORKLOAD["len_seed"]), seed=EMBED_WORKLOAD["chain_seed"])
+            v, cores, sample = cpu_embed_throughput(structures, synth.synthetic_state_dict(EMBED_WORKLOAD["weight_seed"]), budget_s=20.0)
+            print(json.dumps({"impl": "reference", "metric": "structures/s (FoldClassNet embedding)", "value": v, "unit": "structures/s",
+                              "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True,
+                              "config": {"workload": "embed", "structures": n},
+                              "cpu_baseline": {"value": v, "unit": "structures/s", "cores": cores, "kind": "port", "sample": sample},
+                              "e2e": {"value": v, "unit": "structures/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+            return 0
+        print(json.dumps(run_embed(args, steps=args.steps or 3, warmup=args.warmup or 3, cpu_baseline=not args.no_cpu_baseline)))
+        return 0
     wl = dict(WORKLOADS[args.workload])
     if args.nq:
         wl["nq"] = args.nq
@@ -421,6 +524,13 @@ def main():
             except Exception as exc:  # an extra must never take the primary line down
                 if rank == 0:
                     extra[w] = {"error": str(exc)[:300]}
+        if world == 1 and not args.nq:
+            try:
+                o = run_embed(args, steps=3, warmup=3, cpu_baseline=not args.no_cpu_baseline)
+                extra["embed"] = {key: o[key] for key in ("metric", "value", "unit", "ms_per_step", "e2e", "roofline", "config",
+                                                          "gpu_launches", "cpu_baseline") if key in o}
+            except Exception as exc:
+                extra["embed"] = {"error": str(exc)[:300]}
     if world > 1:
         import torch.distributed as dist
 

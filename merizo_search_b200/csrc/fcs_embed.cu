@@ -202,14 +202,11 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) embed_edge_kernel(const EdgeP
             cp_async16(dst + e * 4, src + e * 4);
         }
     };
-    auto gen_h_chunk = [&](int kc, int buf, float d2) {
-        float* dst = sH + buf * (KC * TP);
-#pragma unroll
-        for (int u = 0; u < KC / 2; ++u) {
-            const int kl = g_kq * (KC / 2) + u, kg = kc * KC + kl;
-            const float x = fmaf(d2, sWd[kg], sP[g_il * EHP + kg] + sQ[g_jl * QS + kg]);
-            dst[kl * TP + g_pair] = silu(x);
-        }
+    // one hidden activation of chunk kc: h[kl][g_pair], kl = g_kq * 8 + u
+    auto gen_h_one = [&](int kc, int buf, float d2, int u) {
+        const int kl = g_kq * (KC / 2) + u, kg = kc * KC + kl;
+        const float x = fmaf(d2, sWd[kg], sP[g_il * EHP + kg] + sQ[g_jl * QS + kg]);
+        sH[buf * (KC * TP) + kl * TP + g_pair] = silu(x);
     };
 
     for (int j0 = 0; j0 < L; j0 += TJ) {
@@ -234,7 +231,8 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) embed_edge_kernel(const EdgeP
         __syncthreads();
         const float g_d2 = sD2[g_pair];
         load_w_chunk(0, 0);
-        gen_h_chunk(0, 0, g_d2);
+#pragma unroll
+        for (int u = 0; u < KC / 2; ++u) gen_h_one(0, 0, g_d2, u);
         cp_async_wait_all();
         __syncthreads();
 
@@ -247,14 +245,16 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) embed_edge_kernel(const EdgeP
 #pragma unroll 1
         for (int kc = 0; kc < NCHUNK; ++kc) {
             const int cur = kc & 1;
-            if (kc + 1 < NCHUNK) {
-                load_w_chunk(kc + 1, cur ^ 1);
-                gen_h_chunk(kc + 1, cur ^ 1, g_d2);
-            }
+            // the next chunk is produced while this one is consumed; its 8 activations per thread are interleaved with the
+            // FMA stream (one every second k-step) so their MUFU / shared-memory latencies hide behind FFMA2 issue.  The last
+            // chunk re-produces itself into the idle buffer: no branch in the loop body, 1/33 wasted generation.
+            const int nxt = (kc + 1 < NCHUNK) ? kc + 1 : kc;
+            load_w_chunk(nxt, cur ^ 1);
             const float* hb = sH + cur * (KC * TP) + my_pair0;
             const float* wb = sW + cur * (KC * EM) + my_ch0;
 #pragma unroll
             for (int kl = 0; kl < KC; ++kl) {
+                if ((kl & 1) == 0) gen_h_one(nxt, cur ^ 1, g_d2, kl >> 1);
                 const ulonglong2 h0 = *reinterpret_cast<const ulonglong2*>(hb + kl * TP);
                 const ulonglong2 h1 = *reinterpret_cast<const ulonglong2*>(hb + kl * TP + 4);
                 const ulonglong2 h2 = *reinterpret_cast<const ulonglong2*>(hb + kl * TP + 8);
