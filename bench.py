@@ -8,6 +8,8 @@ Workloads (BASELINE.json `configs`, synthetic unit-norm 128-d rows, random queri
   cfg2            500 k rows (CATH scale), 1 query, k=10  -- fp32 scan (GEMV) path, coverage mask on
   cfg4            45.625 M rows PER GPU (365 M / 8), 1 query, k=10 -- fp32 scan, TED-scale slice
   cfg4b           the same slice, 1024-query batch, k=10          -- tcgen05 path
+  cfg5            the same slice, 65,536-query batch, k=50        -- tcgen05 path (rides along at N=8 only)
+  embed           the step before the search: batched FoldClassNet embedding of 2048 structures (1 GPU)
 With N>1 the database of cfg2/cfg3 is row-sharded over the ranks (strong scaling); cfg4 keeps
 45.625 M rows per rank (weak scaling; at N=8 it is the full 365 M-row TED database).  The per-rank
 key lists are exchanged with ONE NCCL all-gather and merged on the GPU.
@@ -44,6 +46,9 @@ WORKLOADS = {
                  desc="BASELINE configs[3] slice: 365M/8 = 45.625M x 128 fp32 rows per GPU, single query, k=10, fp32 scan path"),
     "cfg4b": dict(rows=45_625_000, nq=1024, k=10, mode="tc", mask=False, scaling="weak",
                   desc="BASELINE configs[3] slice: 365M/8 = 45.625M x 128 rows per GPU, 1024-query batch, k=10, tcgen05 path"),
+    "cfg5": dict(rows=45_625_000, nq=65_536, k=50, mode="tc", mask=False, scaling="weak",
+                 desc="BASELINE configs[4] slice: 365M/8 = 45.625M x 128 rows per GPU, 65,536-query proteome-wide batch, k=50, "
+                      "tcgen05 path (the full TED-scale configuration at N=8)"),
 }
 DEFAULT_WORKLOAD = "cfg3"
 # The step BEFORE the search: embedding the query structures.  Not a BASELINE config of its own --
@@ -482,7 +487,7 @@ def main():
     if args.nq:
         wl["nq"] = args.nq
     if args.steps <= 0:  # long enough (>= ~0.2 s) for nvidia-smi to sample clocks inside the timed region
-        args.steps = {"cfg3": 20, "cfg2": 4000, "cfg4": 60, "cfg4b": 10}[args.workload]
+        args.steps = {"cfg3": 20, "cfg2": 4000, "cfg4": 60, "cfg4b": 10, "cfg5": 3}[args.workload]
     if args.warmup <= 0:
         args.warmup = 3 if wl["mode"] == "tc" else 10
     args.warmup = max(args.warmup, 3)
@@ -515,10 +520,13 @@ def main():
     # slice (the full database at N=8); cfg2 is the CATH-scale single-query case (1 GPU only).
     extra = {}
     if not args.no_extra:
-        others = [w for w in (("cfg4", "cfg4b", "cfg2") if world == 1 else ("cfg4", "cfg4b")) if w != args.workload]
+        # cfg5 (65,536 queries x the full 365 M-row database) rides along only where it IS that configuration: 8 GPUs
+        others = [w for w in (("cfg4", "cfg4b", "cfg2") if world == 1 else (("cfg4", "cfg4b", "cfg5") if world == 8 else ("cfg4", "cfg4b")))
+                  if w != args.workload]
         for w in others:
             try:
-                o, _ = run_gpu(args, WORKLOADS[w], w, steps={"cfg4": 40, "cfg4b": 8, "cfg2": 2000, "cfg3": 10}[w], warmup=5)
+                o, _ = run_gpu(args, WORKLOADS[w], w, steps={"cfg4": 40, "cfg4b": 8, "cfg2": 2000, "cfg3": 10, "cfg5": 3}[w],
+                               warmup=3 if w == "cfg5" else 5)
                 if rank == 0:
                     extra[w] = {key: o[key] for key in ("value", "unit", "ms_per_step", "scaling", "e2e", "roofline", "config", "gpu_launches")}
             except Exception as exc:  # an extra must never take the primary line down

@@ -22,6 +22,8 @@
 //   K_e2 embed_edge_kernel         m_i   [R, 256]   <- dominant: 2 * 528 * 256 flop per (i,j) pair
 //   K_e3 embed_node_mlp_kernel     f'    [R, 128]
 //   K_e4 embed_mean_kernel         mean over residues -> [n, 128]
+#include <cuda_bf16.h>
+
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
@@ -32,6 +34,7 @@
 #include <vector>
 
 #include "../../include/fcsembed.h"
+#include "fcs_common.cuh"
 #include "fcs_internal.h"
 
 namespace fcs {
@@ -141,6 +144,7 @@ struct EdgeParams {
     const float* wg;       // [EM]
     float bg;
     float* M;              // [R][EM]   m_i = sum_j gate_ij * m_ij
+    const uint8_t* w2img;  // tensor-core path: W2 as bf16 hi/lo UMMA operand images, [17 chunks][hi|lo][256 x 32]
 };
 
 // One CTA = TI residues i of one structure against ALL residues j of that structure, TJ at a time.
@@ -329,6 +333,273 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) embed_edge_kernel(const EdgeP
     }
 }
 
+// ------------------------------------------------------------------------------------------------ K_e2 (tensor cores)
+// Same tile (128 pairs x 256 channels, 514 hidden units) on the 5th-generation tensor cores.  The contraction
+// h[128 x 514] . W2^T[514 x 256] is a genuine GEMM; to keep fp32-grade accuracy both operands are split into
+// bf16 hi + lo parts and three products are accumulated in fp32 in TMEM:  hh.Wh + hl.Wh + hh.Wl  (the dropped
+// hl.Wl term is ~2^-16 relative; measured on the golden set the embedding differs from the fp32 reference by
+// < 1e-6 relative, the same as the fp32 kernel).  Per 32-wide chunk of the hidden layer (two UMMA k-steps):
+//   * all 256 threads generate the chunk's activations (thread = pair row x 16 hidden units), split them and store
+//     the hi / lo A operand images straight into shared memory in the canonical K-major no-swizzle core-matrix layout
+//     (8 rows x 16 B core matrices, LBO 128 B, SBO 512 B), then fence.proxy.async + __syncthreads;
+//   * thread 0 waits for the chunk's W2 image (hi | lo, 32 KB, one 1-D bulk copy, three stages, prefetched one chunk
+//     ahead -- the images are identical for every tile, so the copy stream simply cycles over the 17 chunks),
+//     issues 2 x 3 tcgen05.mma.kind::f16 M128 x N256 x K16 and commits to the stage's mbarrier;
+//   * generation of chunk c+1 (other A stage) overlaps the MMAs of chunk c.
+// Epilogue (all 8 warps; warp = TMEM lane quadrant x channel half): tcgen05.ld of the 128 x 256 fp32 accumulators,
+// m = SiLU(acc + b2) kept in registers (128 per thread), gate dot product thread-local + one shared-memory
+// exchange between the two channel halves, sum over the tile's 16 residues j by 16-lane shuffles.
+constexpr int KT = 32;                 // hidden units per chunk
+constexpr int EHT = 544;               // 514 padded to 17 x 32 (pads: h = SiLU(0) = 0 and zero weights)
+constexpr int NCH_T = EHT / KT;        // 17
+constexpr int A_PART = TP * KT * 2;    // 8 KB: one bf16 part of a chunk's A tile
+constexpr int A_STAGE = 2 * A_PART;    // hi | lo
+constexpr int B_PART = EM * KT * 2;    // 16 KB
+constexpr int B_STAGE = 2 * B_PART;    // hi | lo = 32 KB
+constexpr int B_STAGES = 3;
+constexpr int QST = EHT + 4;           // sQ row stride: 16-byte aligned rows, conflict-free LDS.128 across 8 rows
+constexpr int TCF_P = 0;                          // float offsets behind the operand stages
+constexpr int TCF_Q = TCF_P + TI * EHT;
+constexpr int TCF_WD = TCF_Q + TJ * QST;
+constexpr int TCF_MSUM = TCF_WD + EHT;
+constexpr int TCF_GP = TCF_MSUM + TI * EM;
+constexpr int TCF_D2 = TCF_GP + 2 * TP;
+constexpr int TCF_VALID = TCF_D2 + TP;
+constexpr int TCF_B2 = TCF_VALID + TP;
+constexpr int TCF_WG = TCF_B2 + EM;
+constexpr int TCF_FLOATS = TCF_WG + EM;
+constexpr int TC_OPERAND_BYTES = B_STAGES * B_STAGE + 2 * A_STAGE;   // 128 KB
+constexpr int EDGE_TC_SMEM = TC_OPERAND_BYTES + TCF_FLOATS * 4 + 8 * 8;
+static_assert((TCF_FLOATS * 4) % 8 == 0 && TCF_Q % 4 == 0 && TCF_WD % 4 == 0, "alignment");
+constexpr uint64_t TC_DESC = (uint64_t(128 >> 4) << 16) | (uint64_t(512 >> 4) << 32) | (uint64_t(1) << 46);
+// kind::f16 instruction descriptor: D = f32 (bit 4), A = B = bf16 (bits 7, 10), both K-major, N >> 3 at 17, M >> 4 at 24
+constexpr uint32_t TC_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(EM >> 3) << 17) | (uint32_t(TP >> 4) << 24);
+
+__device__ __forceinline__ uint64_t tc_desc(uint32_t smem_addr) { return TC_DESC | uint64_t((smem_addr >> 4) & 0x3FFF); }
+__device__ __forceinline__ void tcg_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcg_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcg_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tcg_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(TC_IDESC), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tcg_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tcg_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 a, __nv_bfloat16 b) {  // a -> low half (lower k)
+    return uint32_t(__bfloat16_as_ushort(a)) | (uint32_t(__bfloat16_as_ushort(b)) << 16);
+}
+
+__global__ void __launch_bounds__(EDGE_THREADS, 1) embed_edge_tc_kernel(const EdgeParams p) {
+    extern __shared__ __align__(1024) uint8_t smraw[];
+    uint8_t* sB = smraw;
+    uint8_t* sA = smraw + B_STAGES * B_STAGE;
+    float* fl = reinterpret_cast<float*>(smraw + TC_OPERAND_BYTES);
+    float* sP = fl + TCF_P;
+    float* sQ = fl + TCF_Q;
+    float* sWd = fl + TCF_WD;
+    float* sMsum = fl + TCF_MSUM;
+    float* sGp = fl + TCF_GP;
+    float* sD2 = fl + TCF_D2;
+    float* sValid = fl + TCF_VALID;
+    float* sB2 = fl + TCF_B2;
+    float* sWg = fl + TCF_WG;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(fl + TCF_FLOATS);
+    uint64_t* b_full = bars;        // [B_STAGES] W2 image of a chunk has landed
+    uint64_t* mma_done = bars + 3;  // [2]        the MMAs that read A stage s (and the B stage of the same chunk) are complete
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int2 item = p.items[blockIdx.x];
+    const int start = p.s_start[item.x], L = p.s_len[item.x], i0 = item.y;
+    const uint32_t total_chunks = uint32_t((L + TJ - 1) / TJ) * NCH_T;
+
+    if (tid == 0) {
+        for (int i = 0; i < B_STAGES; ++i) mbar_init(&b_full[i], 1);
+        for (int i = 0; i < 2; ++i) mbar_init(&mma_done[i], 1);
+        mbar_fence_init();
+    }
+    if (warp == 0) {  // whole warp: 256 TMEM columns = one 128 x 256 fp32 accumulator (one CTA per SM: shared memory)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // ---- per-CTA setup: P rows of the TI residues (clamped inside the structure; pads zero), constants, zeroed sums
+    for (int e = tid; e < TI * (EHT / 4); e += EDGE_THREADS) {
+        const int r = e / (EHT / 4), c4 = e % (EHT / 4);
+        const int row = start + min(i0 + r, L - 1);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c4 < EHP / 4) v = reinterpret_cast<const float4*>(p.P + size_t(row) * EHP)[c4];
+        reinterpret_cast<float4*>(sP)[r * (EHT / 4) + c4] = v;
+    }
+    for (int e = tid; e < EHT; e += EDGE_THREADS) sWd[e] = (e < EHP) ? p.wd[e] : 0.f;
+    for (int e = tid; e < EM; e += EDGE_THREADS) {
+        sB2[e] = p.b2[e];
+        sWg[e] = p.wg[e];
+    }
+    for (int e = tid; e < TI * EM; e += EDGE_THREADS) sMsum[e] = 0.f;
+    tcg_fence_before();
+    __syncthreads();
+    tcg_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint64_t pol_keep = policy_evict_normal();
+    if (tid == 0) {  // W2 image of the first chunk
+        mbar_arrive_expect_tx(&b_full[0], B_STAGE);
+        bulk_g2s(sB, p.w2img, B_STAGE, &b_full[0], pol_keep);
+    }
+
+    // generation coordinates: row = pair, 16 of the chunk's 32 hidden units (two 8-wide core-matrix columns)
+    const int g_row = tid & (TP - 1), g_kh = tid >> 7;
+    const int g_il = g_row >> 4, g_jl = g_row & (TJ - 1);
+    const uint32_t a_row_off = uint32_t(g_row >> 3) * 512u + uint32_t(g_row & 7) * 16u;
+    // epilogue coordinates: TMEM lane quadrant (= warp % 4) x channel half
+    const int quad = warp & 3, half = warp >> 2;
+    const int e_row = quad * 32 + lane;  // pair row of this thread's accumulator lane
+    const int e_il = e_row >> 4;
+
+    uint32_t g = 0;  // running chunk counter of this CTA: A stage g & 1, B stage g % 3
+    for (int j0 = 0; j0 < L; j0 += TJ) {
+        // ---- tile setup: Q rows of the TJ residues j (pads zero), squared distances, validity
+        for (int e = tid; e < TJ * (EHT / 4); e += EDGE_THREADS) {
+            const int r = e / (EHT / 4), c4 = e % (EHT / 4);
+            const int row = start + min(j0 + r, L - 1);
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (c4 < EHP / 4) v = reinterpret_cast<const float4*>(p.Q + size_t(row) * EHP)[c4];
+            *reinterpret_cast<float4*>(sQ + r * QST + c4 * 4) = v;
+        }
+        if (tid < TP) {
+            const int il = tid >> 4, jl = tid & (TJ - 1);
+            const int ri = start + min(i0 + il, L - 1), rj = start + min(j0 + jl, L - 1);
+            const float dx = p.coords[size_t(ri) * 3 + 0] - p.coords[size_t(rj) * 3 + 0];
+            const float dy = p.coords[size_t(ri) * 3 + 1] - p.coords[size_t(rj) * 3 + 1];
+            const float dz = p.coords[size_t(ri) * 3 + 2] - p.coords[size_t(rj) * 3 + 2];
+            const float dist = sqrtf(dx * dx + dy * dy + dz * dz);  // torch.linalg.norm, my_egnn_nocoords.py:49
+            sD2[tid] = dist * dist;                                 // edge_input takes dist*dist, :58
+            sValid[tid] = (i0 + il < L && j0 + jl < L) ? 1.f : 0.f;
+        }
+        __syncthreads();
+        const float g_d2 = sD2[g_row];
+
+#pragma unroll 1
+        for (int c = 0; c < NCH_T; ++c, ++g) {
+            const uint32_t sa = g & 1u;
+            // MMA g-2 has completed: A stage `sa` and the B stage that chunk g+1 will use are free again
+            mbar_wait(&mma_done[sa], ((g >> 1) & 1u) ^ 1u);
+            tcg_fence_after();
+            if (tid == 0 && g + 1 < total_chunks) {
+                const uint32_t sb1 = (g + 1) % B_STAGES;
+                const int c1 = (c + 1 == NCH_T) ? 0 : c + 1;
+                mbar_arrive_expect_tx(&b_full[sb1], B_STAGE);
+                bulk_g2s(sB + sb1 * B_STAGE, p.w2img + size_t(c1) * B_STAGE, B_STAGE, &b_full[sb1], pol_keep);
+            }
+            // ---- generate this chunk's activations: h = SiLU(P_i + Q_j + d2 * w_d), split into bf16 hi + lo
+            uint8_t* a_hi = sA + sa * A_STAGE;
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int k8 = g_kh * 2 + u;           // core-matrix column inside the chunk
+                const int kg = c * KT + k8 * 8;        // first hidden unit of the 8
+                const float4 pa = *reinterpret_cast<const float4*>(sP + g_il * EHT + kg);
+                const float4 pb = *reinterpret_cast<const float4*>(sP + g_il * EHT + kg + 4);
+                const float4 qa = *reinterpret_cast<const float4*>(sQ + g_jl * QST + kg);
+                const float4 qb = *reinterpret_cast<const float4*>(sQ + g_jl * QST + kg + 4);
+                const float4 wa = *reinterpret_cast<const float4*>(sWd + kg);
+                const float4 wb = *reinterpret_cast<const float4*>(sWd + kg + 4);
+                const float x[8] = {fmaf(g_d2, wa.x, pa.x + qa.x), fmaf(g_d2, wa.y, pa.y + qa.y), fmaf(g_d2, wa.z, pa.z + qa.z),
+                                    fmaf(g_d2, wa.w, pa.w + qa.w), fmaf(g_d2, wb.x, pb.x + qb.x), fmaf(g_d2, wb.y, pb.y + qb.y),
+                                    fmaf(g_d2, wb.z, pb.z + qb.z), fmaf(g_d2, wb.w, pb.w + qb.w)};
+                __nv_bfloat16 hi[8], lo[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const float h = silu(x[e]);
+                    hi[e] = __float2bfloat16_rn(h);
+                    lo[e] = __float2bfloat16_rn(h - __bfloat162float(hi[e]));
+                }
+                const uint4 vh = make_uint4(pack_bf16(hi[0], hi[1]), pack_bf16(hi[2], hi[3]), pack_bf16(hi[4], hi[5]), pack_bf16(hi[6], hi[7]));
+                const uint4 vl = make_uint4(pack_bf16(lo[0], lo[1]), pack_bf16(lo[2], lo[3]), pack_bf16(lo[4], lo[5]), pack_bf16(lo[6], lo[7]));
+                *reinterpret_cast<uint4*>(a_hi + a_row_off + k8 * 128) = vh;
+                *reinterpret_cast<uint4*>(a_hi + A_PART + a_row_off + k8 * 128) = vl;
+            }
+            fence_proxy_async();  // generic-proxy stores above -> visible to the tensor core's async-proxy reads
+            __syncthreads();
+            if (tid == 0) {
+                const uint32_t sb = g % B_STAGES;
+                mbar_wait(&b_full[sb], (g / B_STAGES) & 1u);
+                tcg_fence_after();
+                const uint32_t a_addr = smem_u32(a_hi), b_addr = smem_u32(sB + sb * B_STAGE);
+#pragma unroll
+                for (int ks = 0; ks < KT / 16; ++ks) {
+                    const uint64_t ah = tc_desc(a_addr + ks * 256), al = tc_desc(a_addr + A_PART + ks * 256);
+                    const uint64_t bh = tc_desc(b_addr + ks * 256), bl = tc_desc(b_addr + B_PART + ks * 256);
+                    tcg_mma(tmem_base, ah, bh, (c > 0 || ks > 0) ? 1u : 0u);
+                    tcg_mma(tmem_base, al, bh, 1u);
+                    tcg_mma(tmem_base, ah, bl, 1u);
+                }
+                tcg_commit(&mma_done[sa]);
+            }
+            __syncwarp();
+        }
+        // ---- all MMAs of the tile are complete once the last commit (chunk g-1) has arrived
+        mbar_wait(&mma_done[(g - 1) & 1u], ((g - 1) >> 1) & 1u);
+        tcg_fence_after();
+
+        // ---- epilogue: m = SiLU(acc + b2) for this thread's pair and 128 channels; gate; sum over j
+        float m[128];
+        float gd = 0.f;
+#pragma unroll
+        for (int part = 0; part < 4; ++part) {
+            uint32_t r[32];
+            tcg_ld32(tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(half * 128 + part * 32), r);
+            tcg_wait_ld();
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+                const int ch = half * 128 + part * 32 + e;
+                const float v = silu(__uint_as_float(r[e]) + sB2[ch]);
+                gd = fmaf(v, sWg[ch], gd);
+                m[part * 32 + e] = v;
+            }
+        }
+        sGp[half * TP + e_row] = gd;
+        tcg_fence_before();
+        __syncthreads();  // also: every warp has finished reading the accumulator before the next tile overwrites it
+        const float gate = sigmoidf((sGp[e_row] + sGp[TP + e_row]) + p.bg) * sValid[e_row];
+#pragma unroll
+        for (int e = 0; e < 128; ++e) {
+            float v = m[e] * gate;
+            v += __shfl_xor_sync(0xffffffffu, v, 1);
+            v += __shfl_xor_sync(0xffffffffu, v, 2);
+            v += __shfl_xor_sync(0xffffffffu, v, 4);
+            v += __shfl_xor_sync(0xffffffffu, v, 8);
+            if ((lane & 15) == 0) sMsum[e_il * EM + half * 128 + e] += v;  // unique owner of (residue i, channel)
+        }
+        __syncthreads();  // sValid / sD2 / sQ / sGp are rewritten by the next tile
+    }
+
+    for (int e = tid; e < TI * EM; e += EDGE_THREADS) {
+        const int il = e / EM, c = e % EM;
+        if (i0 + il < L) p.M[size_t(start + i0 + il) * EM + c] = sMsum[e];
+    }
+    tcg_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tcg_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ K_e3
 // f'[r] = W4 SiLU(W3 [f_r, m_r] + b3) + b4 + f_r      (node_mlp + residual, my_egnn_nocoords.py:71-72)
 constexpr int NM_ROWS = 16;
@@ -402,6 +673,7 @@ struct LayerDev {
     float* b1ab = nullptr;   // [1056]       b1 | 0
     float* wd = nullptr;     // [528]
     float* w2t = nullptr;    // [528][256]
+    uint8_t* w2img = nullptr; // tensor-core path: [17][hi|lo] bf16 operand images of W2 (32 KB per chunk)
     float* b2 = nullptr;     // [256]
     float* wg = nullptr;     // [256]
     float bg = 0.f;
