@@ -27,6 +27,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <numeric>
@@ -706,6 +707,7 @@ struct fcs_embedder {
     int *s_start = nullptr, *s_len = nullptr;
     int2* items = nullptr;
     fcs_embed_timing timing = {};
+    int mode = FCS_EMBED_MODE_FP32;  // which edge kernel runs (fcs_embed_set_mode)
 };
 
 namespace {
@@ -768,6 +770,22 @@ int upload_layer(LayerDev& d, const fcs_egnn_weights& w) {
     for (int c = 0; c < EW; ++c)
         for (int k = 0; k < EM; ++k) w4t[size_t(k) * EW + c] = w.node_w2[size_t(c) * EM + k];
     d.bg = w.gate_b[0];
+    // tensor-core path: W2 [256 out][514 in] as bf16 hi + lo operand images, one 32 KB block per 32-wide chunk of the
+    // hidden layer, each part in the canonical K-major no-swizzle core-matrix layout (8 rows x 16 B, LBO 128 B, SBO 512 B)
+    std::vector<uint8_t> img(size_t(NCH_T) * B_STAGE, 0);
+    for (int c = 0; c < NCH_T; ++c)
+        for (int n = 0; n < EM; ++n)
+            for (int k = 0; k < KT; ++k) {
+                const int kg = c * KT + k;
+                const float v = kg < EH ? w.edge_w2[size_t(n) * EH + kg] : 0.f;
+                const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+                const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+                const size_t off = size_t(c) * B_STAGE + size_t(n >> 3) * 512 + size_t(k >> 3) * 128 + size_t(n & 7) * 16 + size_t(k & 7) * 2;
+                memcpy(&img[off], &hi, 2);
+                memcpy(&img[off + B_PART], &lo, 2);
+            }
+    EMB_CUDA(cudaMalloc(&d.w2img, img.size()));
+    EMB_CUDA(cudaMemcpy(d.w2img, img.data(), img.size(), cudaMemcpyHostToDevice));
     int rc;
     if ((rc = upload(&d.w1abt, w1abt)) || (rc = upload(&d.b1ab, b1ab)) || (rc = upload(&d.wd, wd)) || (rc = upload(&d.w2t, w2t)) ||
         (rc = upload(&d.b2, b2)) || (rc = upload(&d.wg, wg)) || (rc = upload(&d.w3t, w3t)) || (rc = upload(&d.b3, b3)) ||
@@ -849,9 +867,13 @@ int run_pass(fcs_embedder* e, const float* coords, const int64_t* offsets, int s
         EdgeParams ep;
         ep.coords = e->coords; ep.s_start = e->s_start; ep.s_len = e->s_len; ep.items = e->items;
         ep.P = e->P; ep.Q = e->Q; ep.wd = w.wd; ep.w2t = w.w2t; ep.b2 = w.b2; ep.wg = w.wg; ep.bg = w.bg; ep.M = e->M;
+        ep.w2img = w.w2img;
         const bool timed = *edge_events < fcs_embedder::MAX_EDGE_EVENTS;
         if (timed) EMB_CUDA(cudaEventRecord(e->edge_ev[2 * *edge_events], st));
-        embed_edge_kernel<<<int(n_items), EDGE_THREADS, EDGE_SMEM, st>>>(ep);
+        if (e->mode == FCS_EMBED_MODE_TC)
+            embed_edge_tc_kernel<<<int(n_items), EDGE_THREADS, EDGE_TC_SMEM, st>>>(ep);
+        else
+            embed_edge_kernel<<<int(n_items), EDGE_THREADS, EDGE_SMEM, st>>>(ep);
         EMB_CUDA(cudaGetLastError());
         if (timed) {
             EMB_CUDA(cudaEventRecord(e->edge_ev[2 * *edge_events + 1], st));
@@ -959,6 +981,8 @@ extern "C" int fcs_embedder_create(int device, const fcs_egnn_weights* layers, i
         if (prop.major < 10) return efail(FCS_ERR_UNSUPPORTED, "fcs_embedder_create: built for sm_100a, device is sm_%d%d", prop.major, prop.minor);
         e->sm_count = prop.multiProcessorCount;
         EMB_CUDA(cudaFuncSetAttribute(embed_edge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, EDGE_SMEM));
+        EMB_CUDA(cudaFuncSetAttribute(embed_edge_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, EDGE_TC_SMEM));
+        if (const char* m = getenv("FCS_EMBED_MODE")) e->mode = (atoi(m) == FCS_EMBED_MODE_TC) ? FCS_EMBED_MODE_TC : FCS_EMBED_MODE_FP32;
         EMB_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
         EMB_CUDA(cudaEventCreate(&e->ev0));
         EMB_CUDA(cudaEventCreate(&e->ev1));
@@ -985,7 +1009,7 @@ extern "C" int fcs_embedder_destroy(fcs_embedder* e) {
     free_workspace(e);
     for (LayerDev& d : e->layers) {
         cudaFree(d.w1abt); cudaFree(d.b1ab); cudaFree(d.wd); cudaFree(d.w2t); cudaFree(d.b2); cudaFree(d.wg);
-        cudaFree(d.w3t); cudaFree(d.b3); cudaFree(d.w4t); cudaFree(d.b4);
+        cudaFree(d.w3t); cudaFree(d.b3); cudaFree(d.w4t); cudaFree(d.b4); cudaFree(d.w2img);
     }
     cudaFree(e->pe);
     if (e->ev0) cudaEventDestroy(e->ev0);
@@ -1005,6 +1029,13 @@ extern "C" int fcs_embed(fcs_embedder* e, const float* coords, const int64_t* of
 extern "C" int fcs_embed_to_device(fcs_embedder* e, const float* coords, const int64_t* offsets, int n, float* out_dev) {
     if (n > 0 && !out_dev) return efail(FCS_ERR_INVALID, "fcs_embed_to_device: out_dev is null");
     return embed_impl(e, coords, offsets, n, nullptr, out_dev);
+}
+
+extern "C" int fcs_embed_set_mode(fcs_embedder* e, int mode) {
+    if (!e) return efail(FCS_ERR_INVALID, "fcs_embed_set_mode: null embedder");
+    if (mode != FCS_EMBED_MODE_FP32 && mode != FCS_EMBED_MODE_TC) return efail(FCS_ERR_INVALID, "fcs_embed_set_mode: unknown mode %d", mode);
+    e->mode = mode;
+    return FCS_OK;
 }
 
 extern "C" int fcs_embed_get_timing(const fcs_embedder* e, fcs_embed_timing* out) {

@@ -21,6 +21,7 @@ OK, ERR_INVALID, ERR_CUDA, ERR_STATE, ERR_UNSUPPORTED, ERR_NOMEM = 0, -1, -2, -3
 DB_NORMALISE_ROWS, DB_KEEP_BF16, DB_HAS_LENGTHS = 1, 2, 4
 QNORM_NONE, QNORM_COSINE, QNORM_L2 = 0, 1, 2
 MODE_AUTO, MODE_GEMV, MODE_TC = 0, 1, 2
+EMBED_MODE_FP32, EMBED_MODE_TC = 0, 1
 
 EXPORTS = [
     "fcs_version", "fcs_last_error", "fcs_device_count", "fcs_db_create", "fcs_db_upload",
@@ -28,7 +29,7 @@ EXPORTS = [
     "fcs_search_device", "fcs_merge_topk", "fcs_get_timing", "fcs_set_profiling", "fcs_debug_tc_approx",
     # include/fcsembed.h
     "fcs_embedder_create", "fcs_embedder_destroy", "fcs_embed", "fcs_embed_to_device", "fcs_embed_get_timing",
-    "fcs_embed_debug_layer",
+    "fcs_embed_debug_layer", "fcs_embed_set_mode",
 ]
 
 
@@ -102,6 +103,7 @@ def load() -> C.CDLL:
     lib.fcs_embed_to_device.argtypes = [vp, vp, vp, i32, vp]
     lib.fcs_embed_get_timing.argtypes = [vp, C.POINTER(EmbedTiming)]
     lib.fcs_embed_debug_layer.argtypes = [vp, vp, i32, i32, vp, vp]
+    lib.fcs_embed_set_mode.argtypes = [vp, i32]
     for name in EXPORTS:
         if name not in ("fcs_last_error",):
             getattr(lib, name).restype = C.c_int
@@ -287,6 +289,10 @@ class Embedder:
         msgs = np.empty((L, 256), dtype=np.float32)
         _check(self._lib.fcs_embed_debug_layer(self._h, _np_ptr(coords), L, int(layer), _np_ptr(feats), _np_ptr(msgs)))
         return feats, msgs
+
+    def set_mode(self, mode: int) -> None:
+        """EMBED_MODE_FP32 (fp32 FMA pipe) or EMBED_MODE_TC (tcgen05, bf16 hi/lo split)."""
+        _check(self._lib.fcs_embed_set_mode(self._h, int(mode)))
 
     def timing(self) -> EmbedTiming:
         t = EmbedTiming()
