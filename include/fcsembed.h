@@ -69,9 +69,9 @@ int fcs_embed(fcs_embedder* e, const float* coords, const int64_t* offsets, int 
 int fcs_embed_to_device(fcs_embedder* e, const float* coords, const int64_t* offsets, int n_structures, float* out_dev);
 
 /* Which kernel evaluates the O(L^2) edge MLP:
- *   FCS_EMBED_MODE_FP32  fp32 FMA pipe (packed FFMA2), the default
  *   FCS_EMBED_MODE_TC    tcgen05 tensor cores, bf16 hi/lo split operands, three products, fp32 accumulation in TMEM
- *                        (fp32-grade accuracy: the same parity tolerance applies) */
+ *                        (fp32-grade accuracy: the same parity tolerance applies); the default
+ *   FCS_EMBED_MODE_FP32  fp32 FMA pipe (packed FFMA2) */
 #define FCS_EMBED_MODE_FP32 0
 #define FCS_EMBED_MODE_TC 1
 int fcs_embed_set_mode(fcs_embedder* e, int mode);

@@ -370,7 +370,7 @@ constexpr int TCF_B2 = TCF_VALID + TP;
 constexpr int TCF_WG = TCF_B2 + EM;
 constexpr int TCF_FLOATS = TCF_WG + EM;
 constexpr int TC_OPERAND_BYTES = B_STAGES * B_STAGE + 2 * A_STAGE;   // 128 KB
-constexpr int EDGE_TC_SMEM = TC_OPERAND_BYTES + TCF_FLOATS * 4 + 8 * 8;
+constexpr int EDGE_TC_SMEM = TC_OPERAND_BYTES + TCF_FLOATS * 4 + 10 * 8;
 static_assert((TCF_FLOATS * 4) % 8 == 0 && TCF_Q % 4 == 0 && TCF_WD % 4 == 0, "alignment");
 constexpr uint64_t TC_DESC = (uint64_t(128 >> 4) << 16) | (uint64_t(512 >> 4) << 32) | (uint64_t(1) << 46);
 // kind::f16 instruction descriptor: D = f32 (bit 4), A = B = bf16 (bits 7, 10), both K-major, N >> 3 at 17, M >> 4 at 24
@@ -406,7 +406,10 @@ __device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 a, __nv_bfloat16 b) 
     return uint32_t(__bfloat16_as_ushort(a)) | (uint32_t(__bfloat16_as_ushort(b)) << 16);
 }
 
-__global__ void __launch_bounds__(EDGE_THREADS, 1) embed_edge_tc_kernel(const EdgeParams p) {
+constexpr int TC_GEN_THREADS = EDGE_THREADS;          // warps 0..7: activation generators, then the tile's epilogue
+constexpr int TC_THREADS_ALL = TC_GEN_THREADS + 32;   // warp 8: one thread streams the W2 images and issues the MMAs
+
+__global__ void __launch_bounds__(TC_THREADS_ALL, 1) embed_edge_tc_kernel(const EdgeParams p) {
     extern __shared__ __align__(1024) uint8_t smraw[];
     uint8_t* sB = smraw;
     uint8_t* sA = smraw + B_STAGES * B_STAGE;
@@ -421,9 +424,10 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) embed_edge_tc_kernel(const Ed
     float* sB2 = fl + TCF_B2;
     float* sWg = fl + TCF_WG;
     uint64_t* bars = reinterpret_cast<uint64_t*>(fl + TCF_FLOATS);
-    uint64_t* b_full = bars;        // [B_STAGES] W2 image of a chunk has landed
+    uint64_t* b_full = bars;        // [B_STAGES] W2 image of a chunk has landed (bulk-copy transaction bytes)
     uint64_t* mma_done = bars + 3;  // [2]        the MMAs that read A stage s (and the B stage of the same chunk) are complete
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+    uint64_t* a_full = bars + 5;    // [2]        the 8 generator warps have written A stage s (one elected arrive per warp)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int2 item = p.items[blockIdx.x];
@@ -432,7 +436,10 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) embed_edge_tc_kernel(const Ed
 
     if (tid == 0) {
         for (int i = 0; i < B_STAGES; ++i) mbar_init(&b_full[i], 1);
-        for (int i = 0; i < 2; ++i) mbar_init(&mma_done[i], 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&mma_done[i], 1);
+            mbar_init(&a_full[i], TC_GEN_THREADS / 32);
+        }
         mbar_fence_init();
     }
     if (warp == 0) {  // whole warp: 256 TMEM columns = one 128 x 256 fp32 accumulator (one CTA per SM: shared memory)
@@ -440,107 +447,45 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) embed_edge_tc_kernel(const Ed
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     // ---- per-CTA setup: P rows of the TI residues (clamped inside the structure; pads zero), constants, zeroed sums
-    for (int e = tid; e < TI * (EHT / 4); e += EDGE_THREADS) {
+    for (int e = tid; e < TI * (EHT / 4); e += TC_THREADS_ALL) {
         const int r = e / (EHT / 4), c4 = e % (EHT / 4);
         const int row = start + min(i0 + r, L - 1);
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (c4 < EHP / 4) v = reinterpret_cast<const float4*>(p.P + size_t(row) * EHP)[c4];
         reinterpret_cast<float4*>(sP)[r * (EHT / 4) + c4] = v;
     }
-    for (int e = tid; e < EHT; e += EDGE_THREADS) sWd[e] = (e < EHP) ? p.wd[e] : 0.f;
-    for (int e = tid; e < EM; e += EDGE_THREADS) {
+    for (int e = tid; e < EHT; e += TC_THREADS_ALL) sWd[e] = (e < EHP) ? p.wd[e] : 0.f;
+    for (int e = tid; e < EM; e += TC_THREADS_ALL) {
         sB2[e] = p.b2[e];
         sWg[e] = p.wg[e];
     }
-    for (int e = tid; e < TI * EM; e += EDGE_THREADS) sMsum[e] = 0.f;
+    for (int e = tid; e < TI * EM; e += TC_THREADS_ALL) sMsum[e] = 0.f;
     tcg_fence_before();
     __syncthreads();
     tcg_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint64_t pol_keep = policy_evict_normal();
-    if (tid == 0) {  // W2 image of the first chunk
-        mbar_arrive_expect_tx(&b_full[0], B_STAGE);
-        bulk_g2s(sB, p.w2img, B_STAGE, &b_full[0], pol_keep);
-    }
 
-    // generation coordinates: row = pair, 16 of the chunk's 32 hidden units (two 8-wide core-matrix columns)
-    const int g_row = tid & (TP - 1), g_kh = tid >> 7;
-    const int g_il = g_row >> 4, g_jl = g_row & (TJ - 1);
-    const uint32_t a_row_off = uint32_t(g_row >> 3) * 512u + uint32_t(g_row & 7) * 16u;
-    // epilogue coordinates: TMEM lane quadrant (= warp % 4) x channel half
-    const int quad = warp & 3, half = warp >> 2;
-    const int e_row = quad * 32 + lane;  // pair row of this thread's accumulator lane
-    const int e_il = e_row >> 4;
-
-    uint32_t g = 0;  // running chunk counter of this CTA: A stage g & 1, B stage g % 3
-    for (int j0 = 0; j0 < L; j0 += TJ) {
-        // ---- tile setup: Q rows of the TJ residues j (pads zero), squared distances, validity
-        for (int e = tid; e < TJ * (EHT / 4); e += EDGE_THREADS) {
-            const int r = e / (EHT / 4), c4 = e % (EHT / 4);
-            const int row = start + min(j0 + r, L - 1);
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (c4 < EHP / 4) v = reinterpret_cast<const float4*>(p.Q + size_t(row) * EHP)[c4];
-            *reinterpret_cast<float4*>(sQ + r * QST + c4 * 4) = v;
-        }
-        if (tid < TP) {
-            const int il = tid >> 4, jl = tid & (TJ - 1);
-            const int ri = start + min(i0 + il, L - 1), rj = start + min(j0 + jl, L - 1);
-            const float dx = p.coords[size_t(ri) * 3 + 0] - p.coords[size_t(rj) * 3 + 0];
-            const float dy = p.coords[size_t(ri) * 3 + 1] - p.coords[size_t(rj) * 3 + 1];
-            const float dz = p.coords[size_t(ri) * 3 + 2] - p.coords[size_t(rj) * 3 + 2];
-            const float dist = sqrtf(dx * dx + dy * dy + dz * dz);  // torch.linalg.norm, my_egnn_nocoords.py:49
-            sD2[tid] = dist * dist;                                 // edge_input takes dist*dist, :58
-            sValid[tid] = (i0 + il < L && j0 + jl < L) ? 1.f : 0.f;
-        }
-        __syncthreads();
-        const float g_d2 = sD2[g_row];
-
-#pragma unroll 1
-        for (int c = 0; c < NCH_T; ++c, ++g) {
-            const uint32_t sa = g & 1u;
-            // MMA g-2 has completed: A stage `sa` and the B stage that chunk g+1 will use are free again
-            mbar_wait(&mma_done[sa], ((g >> 1) & 1u) ^ 1u);
-            tcg_fence_after();
-            if (tid == 0 && g + 1 < total_chunks) {
-                const uint32_t sb1 = (g + 1) % B_STAGES;
-                const int c1 = (c + 1 == NCH_T) ? 0 : c + 1;
-                mbar_arrive_expect_tx(&b_full[sb1], B_STAGE);
-                bulk_g2s(sB + sb1 * B_STAGE, p.w2img + size_t(c1) * B_STAGE, B_STAGE, &b_full[sb1], pol_keep);
-            }
-            // ---- generate this chunk's activations: h = SiLU(P_i + Q_j + d2 * w_d), split into bf16 hi + lo
-            uint8_t* a_hi = sA + sa * A_STAGE;
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const int k8 = g_kh * 2 + u;           // core-matrix column inside the chunk
-                const int kg = c * KT + k8 * 8;        // first hidden unit of the 8
-                const float4 pa = *reinterpret_cast<const float4*>(sP + g_il * EHT + kg);
-                const float4 pb = *reinterpret_cast<const float4*>(sP + g_il * EHT + kg + 4);
-                const float4 qa = *reinterpret_cast<const float4*>(sQ + g_jl * QST + kg);
-                const float4 qb = *reinterpret_cast<const float4*>(sQ + g_jl * QST + kg + 4);
-                const float4 wa = *reinterpret_cast<const float4*>(sWd + kg);
-                const float4 wb = *reinterpret_cast<const float4*>(sWd + kg + 4);
-                const float x[8] = {fmaf(g_d2, wa.x, pa.x + qa.x), fmaf(g_d2, wa.y, pa.y + qa.y), fmaf(g_d2, wa.z, pa.z + qa.z),
-                                    fmaf(g_d2, wa.w, pa.w + qa.w), fmaf(g_d2, wb.x, pb.x + qb.x), fmaf(g_d2, wb.y, pb.y + qb.y),
-                                    fmaf(g_d2, wb.z, pb.z + qb.z), fmaf(g_d2, wb.w, pb.w + qb.w)};
-                __nv_bfloat16 hi[8], lo[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const float h = silu(x[e]);
-                    hi[e] = __float2bfloat16_rn(h);
-                    lo[e] = __float2bfloat16_rn(h - __bfloat162float(hi[e]));
+    if (warp == TC_GEN_THREADS / 32) {
+        // ---------------------------------------------------------------- W2 image stream + MMA issue (one thread)
+        if (lane == 0) {
+            const uint64_t pol_keep = policy_evict_normal();
+            mbar_arrive_expect_tx(&b_full[0], B_STAGE);
+            bulk_g2s(sB, p.w2img, B_STAGE, &b_full[0], pol_keep);
+            int c = 0;
+            for (uint32_t g = 0; g < total_chunks; ++g) {
+                const uint32_t sa = g & 1u, sb = g % B_STAGES;
+                // MMA g-2 complete: the B stage chunk g+1 will use is free (the images cycle over the 17 chunks of W2)
+                mbar_wait(&mma_done[sa], ((g >> 1) & 1u) ^ 1u);
+                if (g + 1 < total_chunks) {
+                    const uint32_t sb1 = (g + 1) % B_STAGES;
+                    const int c1 = (c + 1 == NCH_T) ? 0 : c + 1;
+                    mbar_arrive_expect_tx(&b_full[sb1], B_STAGE);
+                    bulk_g2s(sB + sb1 * B_STAGE, p.w2img + size_t(c1) * B_STAGE, B_STAGE, &b_full[sb1], pol_keep);
                 }
-                const uint4 vh = make_uint4(pack_bf16(hi[0], hi[1]), pack_bf16(hi[2], hi[3]), pack_bf16(hi[4], hi[5]), pack_bf16(hi[6], hi[7]));
-                const uint4 vl = make_uint4(pack_bf16(lo[0], lo[1]), pack_bf16(lo[2], lo[3]), pack_bf16(lo[4], lo[5]), pack_bf16(lo[6], lo[7]));
-                *reinterpret_cast<uint4*>(a_hi + a_row_off + k8 * 128) = vh;
-                *reinterpret_cast<uint4*>(a_hi + A_PART + a_row_off + k8 * 128) = vl;
-            }
-            fence_proxy_async();  // generic-proxy stores above -> visible to the tensor core's async-proxy reads
-            __syncthreads();
-            if (tid == 0) {
-                const uint32_t sb = g % B_STAGES;
-                mbar_wait(&b_full[sb], (g / B_STAGES) & 1u);
-                tcg_fence_after();
-                const uint32_t a_addr = smem_u32(a_hi), b_addr = smem_u32(sB + sb * B_STAGE);
+                mbar_wait(&a_full[sa], (g >> 1) & 1u);       // activations of chunk g are in A stage sa ...
+                mbar_wait(&b_full[sb], (g / B_STAGES) & 1u);  // ... and its W2 image in B stage sb
+                tcg_fence_after();  // also orders the epilogue's TMEM reads of the previous tile before the overwrite below
+                const uint32_t a_addr = smem_u32(sA + sa * A_STAGE), b_addr = smem_u32(sB + sb * B_STAGE);
 #pragma unroll
                 for (int ks = 0; ks < KT / 16; ++ks) {
                     const uint64_t ah = tc_desc(a_addr + ks * 256), al = tc_desc(a_addr + A_PART + ks * 256);
@@ -550,51 +495,141 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) embed_edge_tc_kernel(const Ed
                     tcg_mma(tmem_base, ah, bl, 1u);
                 }
                 tcg_commit(&mma_done[sa]);
+                c = (c + 1 == NCH_T) ? 0 : c + 1;
             }
-            __syncwarp();
         }
-        // ---- all MMAs of the tile are complete once the last commit (chunk g-1) has arrived
-        mbar_wait(&mma_done[(g - 1) & 1u], ((g - 1) >> 1) & 1u);
-        tcg_fence_after();
+        __syncwarp();
+    } else {
+        // ---------------------------------------------------------------- generators (thread = pair row x 16 hidden units)
+        const int g_row = tid & (TP - 1), g_kh = tid >> 7;
+        const int g_il = g_row >> 4, g_jl = g_row & (TJ - 1);
+        const uint32_t a_row_off = uint32_t(g_row >> 3) * 512u + uint32_t(g_row & 7) * 16u;
+        // epilogue coordinates: TMEM lane quadrant (= warp % 4) x channel half
+        const int quad = warp & 3, half = warp >> 2;
+        const int e_row = quad * 32 + lane;  // pair row of this thread's accumulator lane
+        const int e_il = e_row >> 4;
 
-        // ---- epilogue: m = SiLU(acc + b2) for this thread's pair and 128 channels; gate; sum over j
-        float m[128];
-        float gd = 0.f;
-#pragma unroll
-        for (int part = 0; part < 4; ++part) {
-            uint32_t r[32];
-            tcg_ld32(tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(half * 128 + part * 32), r);
-            tcg_wait_ld();
-#pragma unroll
-            for (int e = 0; e < 32; ++e) {
-                const int ch = half * 128 + part * 32 + e;
-                const float v = silu(__uint_as_float(r[e]) + sB2[ch]);
-                gd = fmaf(v, sWg[ch], gd);
-                m[part * 32 + e] = v;
+        uint32_t g = 0;  // running chunk counter of this CTA: A stage g & 1
+        for (int j0 = 0; j0 < L; j0 += TJ) {
+            // ---- tile setup: Q rows of the TJ residues j (pads zero), squared distances, validity
+            for (int e = tid; e < TJ * (EHT / 4); e += TC_GEN_THREADS) {
+                const int r = e / (EHT / 4), c4 = e % (EHT / 4);
+                const int row = start + min(j0 + r, L - 1);
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (c4 < EHP / 4) v = reinterpret_cast<const float4*>(p.Q + size_t(row) * EHP)[c4];
+                *reinterpret_cast<float4*>(sQ + r * QST + c4 * 4) = v;
             }
-        }
-        sGp[half * TP + e_row] = gd;
-        tcg_fence_before();
-        __syncthreads();  // also: every warp has finished reading the accumulator before the next tile overwrites it
-        const float gate = sigmoidf((sGp[e_row] + sGp[TP + e_row]) + p.bg) * sValid[e_row];
+            if (tid < TP) {
+                const int il = tid >> 4, jl = tid & (TJ - 1);
+                const int ri = start + min(i0 + il, L - 1), rj = start + min(j0 + jl, L - 1);
+                const float dx = p.coords[size_t(ri) * 3 + 0] - p.coords[size_t(rj) * 3 + 0];
+                const float dy = p.coords[size_t(ri) * 3 + 1] - p.coords[size_t(rj) * 3 + 1];
+                const float dz = p.coords[size_t(ri) * 3 + 2] - p.coords[size_t(rj) * 3 + 2];
+                const float dist = sqrtf(dx * dx + dy * dy + dz * dz);  // torch.linalg.norm, my_egnn_nocoords.py:49
+                sD2[tid] = dist * dist;                                 // edge_input takes dist*dist, :58
+                sValid[tid] = (i0 + il < L && j0 + jl < L) ? 1.f : 0.f;
+            }
+            named_bar_sync(1, TC_GEN_THREADS);
+            const float g_d2 = sD2[g_row];
+
+#pragma unroll 1
+            for (int c = 0; c < NCH_T; ++c, ++g) {
+                const uint32_t sa = g & 1u;
+                mbar_wait(&mma_done[sa], ((g >> 1) & 1u) ^ 1u);  // MMA g-2 has completed: A stage `sa` is free again
+                // ---- this chunk's activations: h = SiLU(P_i + Q_j + d2 * w_d), split into bf16 hi + lo
+                uint8_t* a_hi = sA + sa * A_STAGE;
 #pragma unroll
-        for (int e = 0; e < 128; ++e) {
-            float v = m[e] * gate;
-            v += __shfl_xor_sync(0xffffffffu, v, 1);
-            v += __shfl_xor_sync(0xffffffffu, v, 2);
-            v += __shfl_xor_sync(0xffffffffu, v, 4);
-            v += __shfl_xor_sync(0xffffffffu, v, 8);
-            if ((lane & 15) == 0) sMsum[e_il * EM + half * 128 + e] += v;  // unique owner of (residue i, channel)
+                for (int u = 0; u < 2; ++u) {
+                    const int k8 = g_kh * 2 + u;           // core-matrix column inside the chunk
+                    const int kg = c * KT + k8 * 8;        // first hidden unit of the 8
+                    const float4 pa = *reinterpret_cast<const float4*>(sP + g_il * EHT + kg);
+                    const float4 pb = *reinterpret_cast<const float4*>(sP + g_il * EHT + kg + 4);
+                    const float4 qa = *reinterpret_cast<const float4*>(sQ + g_jl * QST + kg);
+                    const float4 qb = *reinterpret_cast<const float4*>(sQ + g_jl * QST + kg + 4);
+                    const float4 wa = *reinterpret_cast<const float4*>(sWd + kg);
+                    const float4 wb = *reinterpret_cast<const float4*>(sWd + kg + 4);
+                    const float x[8] = {fmaf(g_d2, wa.x, pa.x + qa.x), fmaf(g_d2, wa.y, pa.y + qa.y), fmaf(g_d2, wa.z, pa.z + qa.z),
+                                        fmaf(g_d2, wa.w, pa.w + qa.w), fmaf(g_d2, wb.x, pb.x + qb.x), fmaf(g_d2, wb.y, pb.y + qb.y),
+                                        fmaf(g_d2, wb.z, pb.z + qb.z), fmaf(g_d2, wb.w, pb.w + qb.w)};
+                    __nv_bfloat16 hi[8], lo[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const float h = silu(x[e]);
+                        hi[e] = __float2bfloat16_rn(h);
+                        lo[e] = __float2bfloat16_rn(h - __bfloat162float(hi[e]));
+                    }
+                    const uint4 vh = make_uint4(pack_bf16(hi[0], hi[1]), pack_bf16(hi[2], hi[3]), pack_bf16(hi[4], hi[5]), pack_bf16(hi[6], hi[7]));
+                    const uint4 vl = make_uint4(pack_bf16(lo[0], lo[1]), pack_bf16(lo[2], lo[3]), pack_bf16(lo[4], lo[5]), pack_bf16(lo[6], lo[7]));
+                    *reinterpret_cast<uint4*>(a_hi + a_row_off + k8 * 128) = vh;
+                    *reinterpret_cast<uint4*>(a_hi + A_PART + a_row_off + k8 * 128) = vl;
+                }
+                fence_proxy_async();  // generic-proxy stores above -> visible to the tensor core's async-proxy reads
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&a_full[sa]);
+            }
+            // ---- all MMAs of the tile are complete once the last commit (chunk g-1) has arrived
+            mbar_wait(&mma_done[(g - 1) & 1u], ((g - 1) >> 1) & 1u);
+            tcg_fence_after();
+
+            // ---- epilogue: m = SiLU(acc + b2) for this thread's pair and 128 channels; gate; sum over j
+            float m[128];
+            float gd = 0.f;
+#pragma unroll
+            for (int part = 0; part < 4; ++part) {
+                uint32_t r[32];
+                tcg_ld32(tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(half * 128 + part * 32), r);
+                tcg_wait_ld();
+#pragma unroll
+                for (int e = 0; e < 32; ++e) {
+                    const int ch = half * 128 + part * 32 + e;
+                    const float v = silu(__uint_as_float(r[e]) + sB2[ch]);
+                    gd = fmaf(v, sWg[ch], gd);
+                    m[part * 32 + e] = v;
+                }
+            }
+            sGp[half * TP + e_row] = gd;
+            tcg_fence_before();  // the accumulator reads above are ordered before the next tile's first MMA (via a_full)
+            named_bar_sync(1, TC_GEN_THREADS);
+            const float gate = sigmoidf((sGp[e_row] + sGp[TP + e_row]) + p.bg) * sValid[e_row];
+            // sum over the tile's 16 residues j = the 16 lanes of a half-warp: transpose-reduce (each step a lane keeps
+            // one half of its channels and receives the partner's sums for that half) -- 120 shuffles instead of 512
+            const bool b3 = (lane & 8) != 0, b2 = (lane & 4) != 0, b1 = (lane & 2) != 0, b0 = (lane & 1) != 0;
+            float t64[64], t32[32], t16[16], t8[8];
+#pragma unroll
+            for (int k = 0; k < 64; ++k) {
+                const float lo_v = m[k] * gate, hi_v = m[k + 64] * gate;
+                const float keep = b3 ? hi_v : lo_v, send = b3 ? lo_v : hi_v;
+                t64[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+            }
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+                const float keep = b2 ? t64[k + 32] : t64[k], send = b2 ? t64[k] : t64[k + 32];
+                t32[k] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+            }
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const float keep = b1 ? t32[k + 16] : t32[k], send = b1 ? t32[k] : t32[k + 16];
+                t16[k] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const float keep = b0 ? t16[k + 8] : t16[k], send = b0 ? t16[k] : t16[k + 8];
+                t8[k] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+            }
+            // this lane now owns 8 channels of residue e_il: unique owner of (residue i, channel) in the CTA
+            const int ch0 = half * 128 + (b3 ? 64 : 0) + (b2 ? 32 : 0) + (b1 ? 16 : 0) + (b0 ? 8 : 0);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) sMsum[e_il * EM + ch0 + k] += t8[k];
+            named_bar_sync(1, TC_GEN_THREADS);  // sValid / sD2 / sQ / sGp are rewritten by the next tile
         }
-        __syncthreads();  // sValid / sD2 / sQ / sGp are rewritten by the next tile
     }
 
-    for (int e = tid; e < TI * EM; e += EDGE_THREADS) {
+    tcg_fence_before();
+    __syncthreads();
+    for (int e = tid; e < TI * EM; e += TC_THREADS_ALL) {
         const int il = e / EM, c = e % EM;
         if (i0 + il < L) p.M[size_t(start + i0 + il) * EM + c] = sMsum[e];
     }
-    tcg_fence_before();
-    __syncthreads();
     if (warp == 0) {
         tcg_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
@@ -707,7 +742,7 @@ struct fcs_embedder {
     int *s_start = nullptr, *s_len = nullptr;
     int2* items = nullptr;
     fcs_embed_timing timing = {};
-    int mode = FCS_EMBED_MODE_FP32;  // which edge kernel runs (fcs_embed_set_mode)
+    int mode = FCS_EMBED_MODE_TC;  // which edge kernel runs (fcs_embed_set_mode; FCS_EMBED_MODE env var at create time)
 };
 
 namespace {
@@ -871,7 +906,7 @@ int run_pass(fcs_embedder* e, const float* coords, const int64_t* offsets, int s
         const bool timed = *edge_events < fcs_embedder::MAX_EDGE_EVENTS;
         if (timed) EMB_CUDA(cudaEventRecord(e->edge_ev[2 * *edge_events], st));
         if (e->mode == FCS_EMBED_MODE_TC)
-            embed_edge_tc_kernel<<<int(n_items), EDGE_THREADS, EDGE_TC_SMEM, st>>>(ep);
+            embed_edge_tc_kernel<<<int(n_items), TC_THREADS_ALL, EDGE_TC_SMEM, st>>>(ep);
         else
             embed_edge_kernel<<<int(n_items), EDGE_THREADS, EDGE_SMEM, st>>>(ep);
         EMB_CUDA(cudaGetLastError());
@@ -982,7 +1017,7 @@ extern "C" int fcs_embedder_create(int device, const fcs_egnn_weights* layers, i
         e->sm_count = prop.multiProcessorCount;
         EMB_CUDA(cudaFuncSetAttribute(embed_edge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, EDGE_SMEM));
         EMB_CUDA(cudaFuncSetAttribute(embed_edge_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, EDGE_TC_SMEM));
-        if (const char* m = getenv("FCS_EMBED_MODE")) e->mode = (atoi(m) == FCS_EMBED_MODE_TC) ? FCS_EMBED_MODE_TC : FCS_EMBED_MODE_FP32;
+        if (const char* m = getenv("FCS_EMBED_MODE")) e->mode = (atoi(m) == FCS_EMBED_MODE_FP32) ? FCS_EMBED_MODE_FP32 : FCS_EMBED_MODE_TC;
         EMB_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
         EMB_CUDA(cudaEventCreate(&e->ev0));
         EMB_CUDA(cudaEventCreate(&e->ev1));
