@@ -357,7 +357,7 @@ constexpr int A_PART = TP * KT * 2;    // 8 KB: one bf16 part of a chunk's A til
 constexpr int A_STAGE = 2 * A_PART;    // hi | lo
 constexpr int B_PART = EM * KT * 2;    // 16 KB
 constexpr int B_STAGE = 2 * B_PART;    // hi | lo = 32 KB
-constexpr int B_STAGES = 3;
+constexpr int B_STAGES = 4;            // W2 images in flight: chunk g consumed, g+1 and g+2 on their way
 constexpr int QST = EHT + 4;           // sQ row stride: 16-byte aligned rows, conflict-free LDS.128 across 8 rows
 constexpr int TCF_P = 0;                          // float offsets behind the operand stages
 constexpr int TCF_Q = TCF_P + TI * EHT;
@@ -369,8 +369,9 @@ constexpr int TCF_VALID = TCF_D2 + TP;
 constexpr int TCF_B2 = TCF_VALID + TP;
 constexpr int TCF_WG = TCF_B2 + EM;
 constexpr int TCF_FLOATS = TCF_WG + EM;
-constexpr int TC_OPERAND_BYTES = B_STAGES * B_STAGE + 2 * A_STAGE;   // 128 KB
+constexpr int TC_OPERAND_BYTES = B_STAGES * B_STAGE + 2 * A_STAGE;   // 160 KB
 constexpr int EDGE_TC_SMEM = TC_OPERAND_BYTES + TCF_FLOATS * 4 + 10 * 8;
+static_assert(EDGE_TC_SMEM <= 232448, "dynamic shared memory limit of sm_100");
 static_assert((TCF_FLOATS * 4) % 8 == 0 && TCF_Q % 4 == 0 && TCF_WD % 4 == 0, "alignment");
 constexpr uint64_t TC_DESC = (uint64_t(128 >> 4) << 16) | (uint64_t(512 >> 4) << 32) | (uint64_t(1) << 46);
 // kind::f16 instruction descriptor: D = f32 (bit 4), A = B = bf16 (bits 7, 10), both K-major, N >> 3 at 17, M >> 4 at 24
@@ -402,8 +403,28 @@ __device__ __forceinline__ void tcg_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         : "memory");
 }
 __device__ __forceinline__ void tcg_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 a, __nv_bfloat16 b) {  // a -> low half (lower k)
-    return uint32_t(__bfloat16_as_ushort(a)) | (uint32_t(__bfloat16_as_ushort(b)) << 16);
+// sigmoid with ONE special-function op: the tensor-core kernel is bound by the XU pipe (16 lanes/clk/SM: MUFU.EX2, MUFU.RCP
+// and F2F conversions share it; ncu: XU 51 % vs tensor 31 %), while the FMA pipe idles.  exp(-|x|) = ex2 on the XU, the
+// reciprocal of 1 + e in (1, 2] by a linear seed (6 % error) and three Newton steps on the FMA pipe (error^2 per step:
+// 3e-3, 1e-5, 1e-10); for x < 0 sigmoid = e / (1 + e).  Max relative error 2e-7 for |x| < 20.
+__device__ __forceinline__ float sigmoid_nr(float x) {
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * fabsf(x)));
+    const float d = 1.f + e;
+    float y = fmaf(d, -0.47058824f, 1.4117647f);
+    y = fmaf(y, fmaf(-d, y, 1.f), y);
+    y = fmaf(y, fmaf(-d, y, 1.f), y);
+    y = fmaf(y, fmaf(-d, y, 1.f), y);
+    return x >= 0.f ? y : e * y;
+}
+__device__ __forceinline__ float silu_nr(float x) { return x * sigmoid_nr(x); }
+// two activations -> packed bf16 hi parts and packed bf16 lo parts (element 0 in the low half); F2FP.PACK_AB runs on the
+// ALU pipe (the scalar F2F.BF16.F32 conversions it replaces ran on the XU pipe)
+__device__ __forceinline__ void split_bf16x2(float h0, float h1, uint32_t& hi, uint32_t& lo) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(h0, h1);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(h0 - __uint_as_float(hi << 16), h1 - __uint_as_float(hi & 0xffff0000u));
+    lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
 constexpr int TC_GEN_THREADS = EDGE_THREADS;          // warps 0..7: activation generators, then the tile's epilogue
@@ -425,9 +446,9 @@ __global__ void __launch_bounds__(TC_THREADS_ALL, 1) embed_edge_tc_kernel(const 
     float* sWg = fl + TCF_WG;
     uint64_t* bars = reinterpret_cast<uint64_t*>(fl + TCF_FLOATS);
     uint64_t* b_full = bars;        // [B_STAGES] W2 image of a chunk has landed (bulk-copy transaction bytes)
-    uint64_t* mma_done = bars + 3;  // [2]        the MMAs that read A stage s (and the B stage of the same chunk) are complete
-    uint64_t* a_full = bars + 5;    // [2]        the 8 generator warps have written A stage s (one elected arrive per warp)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
+    uint64_t* mma_done = bars + 4;  // [2]        the MMAs that read A stage s (and the B stage of the same chunk) are complete
+    uint64_t* a_full = bars + 6;    // [2]        the 8 generator warps have written A stage s (one elected arrive per warp)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int2 item = p.items[blockIdx.x];
@@ -469,18 +490,20 @@ __global__ void __launch_bounds__(TC_THREADS_ALL, 1) embed_edge_tc_kernel(const 
         // ---------------------------------------------------------------- W2 image stream + MMA issue (one thread)
         if (lane == 0) {
             const uint64_t pol_keep = policy_evict_normal();
-            mbar_arrive_expect_tx(&b_full[0], B_STAGE);
-            bulk_g2s(sB, p.w2img, B_STAGE, &b_full[0], pol_keep);
+            for (uint32_t g0 = 0; g0 < 2 && g0 < total_chunks; ++g0) {  // images of the first two chunks
+                mbar_arrive_expect_tx(&b_full[g0], B_STAGE);
+                bulk_g2s(sB + g0 * B_STAGE, p.w2img + size_t(g0) * B_STAGE, B_STAGE, &b_full[g0], pol_keep);
+            }
             int c = 0;
             for (uint32_t g = 0; g < total_chunks; ++g) {
                 const uint32_t sa = g & 1u, sb = g % B_STAGES;
-                // MMA g-2 complete: the B stage chunk g+1 will use is free (the images cycle over the 17 chunks of W2)
+                // MMA g-2 complete: its B stage is free for chunk g+2 (the images cycle over the 17 chunks of W2)
                 mbar_wait(&mma_done[sa], ((g >> 1) & 1u) ^ 1u);
-                if (g + 1 < total_chunks) {
-                    const uint32_t sb1 = (g + 1) % B_STAGES;
-                    const int c1 = (c + 1 == NCH_T) ? 0 : c + 1;
-                    mbar_arrive_expect_tx(&b_full[sb1], B_STAGE);
-                    bulk_g2s(sB + sb1 * B_STAGE, p.w2img + size_t(c1) * B_STAGE, B_STAGE, &b_full[sb1], pol_keep);
+                if (g + 2 < total_chunks) {
+                    const uint32_t sb2 = (g + 2) % B_STAGES;
+                    const int c2 = (c + 2 >= NCH_T) ? c + 2 - NCH_T : c + 2;
+                    mbar_arrive_expect_tx(&b_full[sb2], B_STAGE);
+                    bulk_g2s(sB + sb2 * B_STAGE, p.w2img + size_t(c2) * B_STAGE, B_STAGE, &b_full[sb2], pol_keep);
                 }
                 mbar_wait(&a_full[sa], (g >> 1) & 1u);       // activations of chunk g are in A stage sa ...
                 mbar_wait(&b_full[sb], (g / B_STAGES) & 1u);  // ... and its W2 image in B stage sb
@@ -551,15 +574,11 @@ __global__ void __launch_bounds__(TC_THREADS_ALL, 1) embed_edge_tc_kernel(const 
                     const float x[8] = {fmaf(g_d2, wa.x, pa.x + qa.x), fmaf(g_d2, wa.y, pa.y + qa.y), fmaf(g_d2, wa.z, pa.z + qa.z),
                                         fmaf(g_d2, wa.w, pa.w + qa.w), fmaf(g_d2, wb.x, pb.x + qb.x), fmaf(g_d2, wb.y, pb.y + qb.y),
                                         fmaf(g_d2, wb.z, pb.z + qb.z), fmaf(g_d2, wb.w, pb.w + qb.w)};
-                    __nv_bfloat16 hi[8], lo[8];
+                    uint32_t hw[4], lw[4];
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        const float h = silu(x[e]);
-                        hi[e] = __float2bfloat16_rn(h);
-                        lo[e] = __float2bfloat16_rn(h - __bfloat162float(hi[e]));
-                    }
-                    const uint4 vh = make_uint4(pack_bf16(hi[0], hi[1]), pack_bf16(hi[2], hi[3]), pack_bf16(hi[4], hi[5]), pack_bf16(hi[6], hi[7]));
-                    const uint4 vl = make_uint4(pack_bf16(lo[0], lo[1]), pack_bf16(lo[2], lo[3]), pack_bf16(lo[4], lo[5]), pack_bf16(lo[6], lo[7]));
+                    for (int e = 0; e < 4; ++e) split_bf16x2(silu_nr(x[2 * e]), silu_nr(x[2 * e + 1]), hw[e], lw[e]);
+                    const uint4 vh = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                    const uint4 vl = make_uint4(lw[0], lw[1], lw[2], lw[3]);
                     *reinterpret_cast<uint4*>(a_hi + a_row_off + k8 * 128) = vh;
                     *reinterpret_cast<uint4*>(a_hi + A_PART + a_row_off + k8 * 128) = vl;
                 }
@@ -582,7 +601,7 @@ __global__ void __launch_bounds__(TC_THREADS_ALL, 1) embed_edge_tc_kernel(const 
 #pragma unroll
                 for (int e = 0; e < 32; ++e) {
                     const int ch = half * 128 + part * 32 + e;
-                    const float v = silu(__uint_as_float(r[e]) + sB2[ch]);
+                    const float v = silu_nr(__uint_as_float(r[e]) + sB2[ch]);
                     gd = fmaf(v, sWg[ch], gd);
                     m[part * 32 + e] = v;
                 }
@@ -590,7 +609,7 @@ __global__ void __launch_bounds__(TC_THREADS_ALL, 1) embed_edge_tc_kernel(const 
             sGp[half * TP + e_row] = gd;
             tcg_fence_before();  // the accumulator reads above are ordered before the next tile's first MMA (via a_full)
             named_bar_sync(1, TC_GEN_THREADS);
-            const float gate = sigmoidf((sGp[e_row] + sGp[TP + e_row]) + p.bg) * sValid[e_row];
+            const float gate = sigmoid_nr((sGp[e_row] + sGp[TP + e_row]) + p.bg) * sValid[e_row];
             // sum over the tile's 16 residues j = the 16 lanes of a half-warp: transpose-reduce (each step a lane keeps
             // one half of its channels and receives the partner's sums for that half) -- 120 shuffles instead of 512
             const bool b3 = (lane & 8) != 0, b2 = (lane & 4) != 0, b1 = (lane & 2) != 0, b0 = (lane & 1) != 0;
