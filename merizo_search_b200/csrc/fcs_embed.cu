@@ -13,13 +13,14 @@
 // P = f W1[:, :128]^T + b1 and Q = f W1[:, 128:256]^T computed once per RESIDUE (K_e1), so the per-PAIR work
 // is one fused kernel (K_e2, embed_edge_kernel): h_ij is generated on the fly in shared memory, contracted
 // with W2 (the only O(L^2 x 514 x 256) term: 263 kFLOP per pair), gated and summed over j in registers /
-// shared memory; only m_i [L,256] is written.  HBM traffic per pair is ~0; the kernel is bound by the fp32
-// FMA pipe (packed FFMA2).  fp32 throughout: the embedding must match the reference network to fp32
-// rounding (tests: max relative error 5e-5 of the largest component, cosine > 1 - 1e-6).
+// shared memory; only m_i [L,256] is written.  HBM traffic per pair is ~0.  The embedding must match the reference
+// network to fp32 rounding (tests: max relative error 5e-5 of the largest component, cosine > 1 - 1e-6), so the
+// contraction is either fp32 (FMA pipe) or bf16 hi/lo split x3 with fp32 accumulation (tensor cores).
 //
 //   K_e0 embed_init_feats_kernel   f = pe[:L]                          (PositionalEncoder.forward)
 //   K_e1 embed_node_proj_kernel    P, Q  [R, 528] (514 padded to 33 x 16)
-//   K_e2 embed_edge_kernel         m_i   [R, 256]   <- dominant: 2 * 528 * 256 flop per (i,j) pair
+//   K_e2 embed_edge_tc_kernel      m_i   [R, 256]   <- dominant; tcgen05 (default): 3 x 2*514*256 bf16 flop per (i,j) pair
+//        embed_edge_kernel                             fp32 FMA-pipe variant (FCS_EMBED_MODE_FP32): 2*514*256 flop per pair
 //   K_e3 embed_node_mlp_kernel     f'    [R, 128]
 //   K_e4 embed_mean_kernel         mean over residues -> [n, 128]
 #include <cuda_bf16.h>

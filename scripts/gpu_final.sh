@@ -4,15 +4,15 @@ mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
 timeout 200 python __graft_entry__.py smoke 2>&1 | tail -2
 timeout 900 python bench.py > gpurun_out/bench_default3.json 2> gpurun_out/bench_default3.err; tail -2 gpurun_out/bench_default3.err
-timeout 600 python bench.py --workload cfg5 --no-cpu-baseline --no-extra > gpurun_out/bench_cfg5.json 2> gpurun_out/bench_cfg5.err; tail -2 gpurun_out/bench_cfg5.err
 timeout 300 python bench.py --workload embed > gpurun_out/bench_embed.json 2> gpurun_out/bench_embed.err; tail -2 gpurun_out/bench_embed.err
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/launches_embed.csv \
     python bench.py --workload embed --nq 512 --steps 1 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:embed_edge -s 6 -c 1 -o gpurun_out/prof_embed_edge \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:embed_edge_tc -s 6 -c 1 -o gpurun_out/prof_embed_edge_tc \
     python bench.py --workload embed --nq 512 --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_embed.log 2>&1
+FCS_EMBED_MODE=0 timeout 300 python bench.py --workload embed --no-cpu-baseline > gpurun_out/bench_embed_fp32.json 2>/dev/null
 python - <<'PY'
 import json
-for f in ("bench_default3", "bench_cfg5", "bench_embed"):
+for f in ("bench_default3", "bench_embed", "bench_embed_fp32"):
     try:
         d = json.loads(open(f"gpurun_out/{f}.json").read().strip().splitlines()[-1])
     except Exception as e:
