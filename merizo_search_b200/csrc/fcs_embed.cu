@@ -347,7 +347,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) embed_edge_kernel(const EdgeP
 //   * thread 0 waits for the chunk's W2 image (hi | lo, 32 KB, one 1-D bulk copy, three stages, prefetched one chunk
 //     ahead -- the images are identical for every tile, so the copy stream simply cycles over the 17 chunks),
 //     issues 2 x 3 tcgen05.mma.kind::f16 M128 x N256 x K16 and commits to the stage's mbarrier;
-//   * generation of chunk c+1 (other A stage) overlaps the MMAs of chunk c.
+//   * three stages of each operand: the generators run up to two chunks ahead of the MMAs.
 // Epilogue (all 8 warps; warp = TMEM lane quadrant x channel half): tcgen05.ld of the 128 x 256 fp32 accumulators,
 // m = SiLU(acc + b2) kept in registers (128 per thread), gate dot product thread-local + one shared-memory
 // exchange between the two channel halves, sum over the tile's 16 residues j by 16-lane shuffles.
@@ -358,7 +358,9 @@ constexpr int A_PART = TP * KT * 2;    // 8 KB: one bf16 part of a chunk's A til
 constexpr int A_STAGE = 2 * A_PART;    // hi | lo
 constexpr int B_PART = EM * KT * 2;    // 16 KB
 constexpr int B_STAGE = 2 * B_PART;    // hi | lo = 32 KB
-constexpr int B_STAGES = 4;            // W2 images in flight: chunk g consumed, g+1 and g+2 on their way
+constexpr int TC_STAGES = 3;           // ring depth of BOTH operands: chunk g uses A stage g % 3 and B stage g % 3
+constexpr int B_STAGES = TC_STAGES;
+constexpr int A_STAGES = TC_STAGES;
 constexpr int QST = EHT + 4;           // sQ row stride: 16-byte aligned rows, conflict-free LDS.128 across 8 rows
 constexpr int TCF_P = 0;                          // float offsets behind the operand stages
 constexpr int TCF_Q = TCF_P + TI * EHT;
@@ -370,8 +372,8 @@ constexpr int TCF_VALID = TCF_D2 + TP;
 constexpr int TCF_B2 = TCF_VALID + TP;
 constexpr int TCF_WG = TCF_B2 + EM;
 constexpr int TCF_FLOATS = TCF_WG + EM;
-constexpr int TC_OPERAND_BYTES = B_STAGES * B_STAGE + 2 * A_STAGE;   // 160 KB
-constexpr int EDGE_TC_SMEM = TC_OPERAND_BYTES + TCF_FLOATS * 4 + 10 * 8;
+constexpr int TC_OPERAND_BYTES = B_STAGES * B_STAGE + A_STAGES * A_STAGE;   // 144 KB
+constexpr int EDGE_TC_SMEM = TC_OPERAND_BYTES + TCF_FLOATS * 4 + 12 * 8;
 static_assert(EDGE_TC_SMEM <= 232448, "dynamic shared memory limit of sm_100");
 static_assert((TCF_FLOATS * 4) % 8 == 0 && TCF_Q % 4 == 0 && TCF_WD % 4 == 0, "alignment");
 constexpr uint64_t TC_DESC = (uint64_t(128 >> 4) << 16) | (uint64_t(512 >> 4) << 32) | (uint64_t(1) << 46);
@@ -446,10 +448,10 @@ __global__ void __launch_bounds__(TC_THREADS_ALL, 1) embed_edge_tc_kernel(const 
     float* sB2 = fl + TCF_B2;
     float* sWg = fl + TCF_WG;
     uint64_t* bars = reinterpret_cast<uint64_t*>(fl + TCF_FLOATS);
-    uint64_t* b_full = bars;        // [B_STAGES] W2 image of a chunk has landed (bulk-copy transaction bytes)
-    uint64_t* mma_done = bars + 4;  // [2]        the MMAs that read A stage s (and the B stage of the same chunk) are complete
-    uint64_t* a_full = bars + 6;    // [2]        the 8 generator warps have written A stage s (one elected arrive per warp)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+    uint64_t* b_full = bars;        // [3] W2 image of a chunk has landed (bulk-copy transaction bytes)
+    uint64_t* mma_done = bars + 3;  // [3] the MMAs that read stage s (A and B of the same chunk) are complete
+    uint64_t* a_full = bars + 6;    // [3] the 8 generator warps have written A stage s (one elected arrive per warp)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int2 item = p.items[blockIdx.x];
@@ -457,8 +459,8 @@ __global__ void __launch_bounds__(TC_THREADS_ALL, 1) embed_edge_tc_kernel(const 
     const uint32_t total_chunks = uint32_t((L + TJ - 1) / TJ) * NCH_T;
 
     if (tid == 0) {
-        for (int i = 0; i < B_STAGES; ++i) mbar_init(&b_full[i], 1);
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < TC_STAGES; ++i) {
+            mbar_init(&b_full[i], 1);
             mbar_init(&mma_done[i], 1);
             mbar_init(&a_full[i], TC_GEN_THREADS / 32);
         }
@@ -491,25 +493,24 @@ __global__ void __launch_bounds__(TC_THREADS_ALL, 1) embed_edge_tc_kernel(const 
         // ---------------------------------------------------------------- W2 image stream + MMA issue (one thread)
         if (lane == 0) {
             const uint64_t pol_keep = policy_evict_normal();
-            for (uint32_t g0 = 0; g0 < 2 && g0 < total_chunks; ++g0) {  // images of the first two chunks
-                mbar_arrive_expect_tx(&b_full[g0], B_STAGE);
-                bulk_g2s(sB + g0 * B_STAGE, p.w2img + size_t(g0) * B_STAGE, B_STAGE, &b_full[g0], pol_keep);
-            }
+            mbar_arrive_expect_tx(&b_full[0], B_STAGE);  // image of the first chunk
+            bulk_g2s(sB, p.w2img, B_STAGE, &b_full[0], pol_keep);
             int c = 0;
             for (uint32_t g = 0; g < total_chunks; ++g) {
-                const uint32_t sa = g & 1u, sb = g % B_STAGES;
-                // MMA g-2 complete: its B stage is free for chunk g+2 (the images cycle over the 17 chunks of W2)
-                mbar_wait(&mma_done[sa], ((g >> 1) & 1u) ^ 1u);
-                if (g + 2 < total_chunks) {
-                    const uint32_t sb2 = (g + 2) % B_STAGES;
-                    const int c2 = (c + 2 >= NCH_T) ? c + 2 - NCH_T : c + 2;
-                    mbar_arrive_expect_tx(&b_full[sb2], B_STAGE);
-                    bulk_g2s(sB + sb2 * B_STAGE, p.w2img + size_t(c2) * B_STAGE, B_STAGE, &b_full[sb2], pol_keep);
+                const uint32_t st = g % TC_STAGES, use = g / TC_STAGES;
+                if (g + 1 < total_chunks) {
+                    // stage of chunk g+1 was last read by MMA g-2: once that has completed, stream the next W2 image in
+                    // (the images cycle over the 17 chunks of W2; MMA g-1 keeps the tensor pipe busy meanwhile)
+                    const uint32_t st1 = (g + 1) % TC_STAGES, use1 = (g + 1) / TC_STAGES;
+                    const int c1 = (c + 1 == NCH_T) ? 0 : c + 1;
+                    mbar_wait(&mma_done[st1], (use1 & 1u) ^ 1u);
+                    mbar_arrive_expect_tx(&b_full[st1], B_STAGE);
+                    bulk_g2s(sB + st1 * B_STAGE, p.w2img + size_t(c1) * B_STAGE, B_STAGE, &b_full[st1], pol_keep);
                 }
-                mbar_wait(&a_full[sa], (g >> 1) & 1u);       // activations of chunk g are in A stage sa ...
-                mbar_wait(&b_full[sb], (g / B_STAGES) & 1u);  // ... and its W2 image in B stage sb
+                mbar_wait(&a_full[st], use & 1u);  // activations of chunk g are in A stage st ...
+                mbar_wait(&b_full[st], use & 1u);  // ... and its W2 image in B stage st
                 tcg_fence_after();  // also orders the epilogue's TMEM reads of the previous tile before the overwrite below
-                const uint32_t a_addr = smem_u32(sA + sa * A_STAGE), b_addr = smem_u32(sB + sb * B_STAGE);
+                const uint32_t a_addr = smem_u32(sA + st * A_STAGE), b_addr = smem_u32(sB + st * B_STAGE);
 #pragma unroll
                 for (int ks = 0; ks < KT / 16; ++ks) {
                     const uint64_t ah = tc_desc(a_addr + ks * 256), al = tc_desc(a_addr + A_PART + ks * 256);
@@ -518,7 +519,7 @@ __global__ void __launch_bounds__(TC_THREADS_ALL, 1) embed_edge_tc_kernel(const 
                     tcg_mma(tmem_base, al, bh, 1u);
                     tcg_mma(tmem_base, ah, bl, 1u);
                 }
-                tcg_commit(&mma_done[sa]);
+                tcg_commit(&mma_done[st]);
                 c = (c + 1 == NCH_T) ? 0 : c + 1;
             }
         }
@@ -533,7 +534,7 @@ __global__ void __launch_bounds__(TC_THREADS_ALL, 1) embed_edge_tc_kernel(const 
         const int e_row = quad * 32 + lane;  // pair row of this thread's accumulator lane
         const int e_il = e_row >> 4;
 
-        uint32_t g = 0;  // running chunk counter of this CTA: A stage g & 1
+        uint32_t g = 0;  // running chunk counter of this CTA: stage g % 3
         for (int j0 = 0; j0 < L; j0 += TJ) {
             // ---- tile setup: Q rows of the TJ residues j (pads zero), squared distances, validity
             for (int e = tid; e < TJ * (EHT / 4); e += TC_GEN_THREADS) {
@@ -558,10 +559,10 @@ __global__ void __launch_bounds__(TC_THREADS_ALL, 1) embed_edge_tc_kernel(const 
 
 #pragma unroll 1
             for (int c = 0; c < NCH_T; ++c, ++g) {
-                const uint32_t sa = g & 1u;
-                mbar_wait(&mma_done[sa], ((g >> 1) & 1u) ^ 1u);  // MMA g-2 has completed: A stage `sa` is free again
+                const uint32_t st = g % TC_STAGES;
+                mbar_wait(&mma_done[st], ((g / TC_STAGES) & 1u) ^ 1u);  // MMA g-3 has completed: A stage `st` is free again
                 // ---- this chunk's activations: h = SiLU(P_i + Q_j + d2 * w_d), split into bf16 hi + lo
-                uint8_t* a_hi = sA + sa * A_STAGE;
+                uint8_t* a_hi = sA + st * A_STAGE;
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
                     const int k8 = g_kh * 2 + u;           // core-matrix column inside the chunk
@@ -585,10 +586,10 @@ __global__ void __launch_bounds__(TC_THREADS_ALL, 1) embed_edge_tc_kernel(const 
                 }
                 fence_proxy_async();  // generic-proxy stores above -> visible to the tensor core's async-proxy reads
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&a_full[sa]);
+                if (lane == 0) mbar_arrive(&a_full[st]);
             }
             // ---- all MMAs of the tile are complete once the last commit (chunk g-1) has arrived
-            mbar_wait(&mma_done[(g - 1) & 1u], ((g - 1) >> 1) & 1u);
+            mbar_wait(&mma_done[(g - 1) % TC_STAGES], ((g - 1) / TC_STAGES) & 1u);
             tcg_fence_after();
 
             // ---- epilogue: m = SiLU(acc + b2) for this thread's pair and 128 channels; gate; sum over j
