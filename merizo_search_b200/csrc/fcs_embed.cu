@@ -406,21 +406,18 @@ __device__ __forceinline__ void tcg_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         : "memory");
 }
 __device__ __forceinline__ void tcg_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-// sigmoid with ONE special-function op: the tensor-core kernel is bound by the XU pipe (16 lanes/clk/SM: MUFU.EX2, MUFU.RCP
-// and F2F conversions share it; ncu: XU 51 % vs tensor 31 %), while the FMA pipe idles.  exp(-|x|) = ex2 on the XU, the
-// reciprocal of 1 + e in (1, 2] by a linear seed (6 % error) and three Newton steps on the FMA pipe (error^2 per step:
-// 3e-3, 1e-5, 1e-10); for x < 0 sigmoid = e / (1 + e).  Max relative error 2e-7 for |x| < 20.
-__device__ __forceinline__ float sigmoid_nr(float x) {
-    float e;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * fabsf(x)));
-    const float d = 1.f + e;
-    float y = fmaf(d, -0.47058824f, 1.4117647f);
-    y = fmaf(y, fmaf(-d, y, 1.f), y);
-    y = fmaf(y, fmaf(-d, y, 1.f), y);
-    y = fmaf(y, fmaf(-d, y, 1.f), y);
-    return x >= 0.f ? y : e * y;
+// SiLU / sigmoid for the tensor-core kernel, which is bound by the instruction rate of its 8 generator warps (2 per
+// scheduler): the cheapest correct form is  sigmoid(x) = rcp(1 + ex2(-x * log2 e))  -- two XU ops (MUFU.EX2, MUFU.RCP; the
+// 16-lane XU pipe has the room since the bf16 conversions moved to the ALU pipe) and no range handling: ex2 overflows to
+// +inf for x < -88 (rcp(inf) = 0, SiLU = -0 like the reference) and flushes to 0 for large x (sigmoid = 1).  A Newton-Raphson
+// reciprocal on the FMA pipe (one XU op per activation) measured the same throughput at 6 more instructions per activation.
+__device__ __forceinline__ float sigmoid_fast(float x) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * x));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));
+    return r;
 }
-__device__ __forceinline__ float silu_nr(float x) { return x * sigmoid_nr(x); }
+__device__ __forceinline__ float silu_fast(float x) { return x * sigmoid_fast(x); }
 // two activations -> packed bf16 hi parts and packed bf16 lo parts (element 0 in the low half); F2FP.PACK_AB runs on the
 // ALU pipe (the scalar F2F.BF16.F32 conversions it replaces ran on the XU pipe)
 __device__ __forceinline__ void split_bf16x2(float h0, float h1, uint32_t& hi, uint32_t& lo) {
@@ -578,7 +575,7 @@ __global__ void __launch_bounds__(TC_THREADS_ALL, 1) embed_edge_tc_kernel(const 
                                         fmaf(g_d2, wb.z, pb.z + qb.z), fmaf(g_d2, wb.w, pb.w + qb.w)};
                     uint32_t hw[4], lw[4];
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) split_bf16x2(silu_nr(x[2 * e]), silu_nr(x[2 * e + 1]), hw[e], lw[e]);
+                    for (int e = 0; e < 4; ++e) split_bf16x2(silu_fast(x[2 * e]), silu_fast(x[2 * e + 1]), hw[e], lw[e]);
                     const uint4 vh = make_uint4(hw[0], hw[1], hw[2], hw[3]);
                     const uint4 vl = make_uint4(lw[0], lw[1], lw[2], lw[3]);
                     *reinterpret_cast<uint4*>(a_hi + a_row_off + k8 * 128) = vh;
@@ -603,7 +600,7 @@ __global__ void __launch_bounds__(TC_THREADS_ALL, 1) embed_edge_tc_kernel(const 
 #pragma unroll
                 for (int e = 0; e < 32; ++e) {
                     const int ch = half * 128 + part * 32 + e;
-                    const float v = silu_nr(__uint_as_float(r[e]) + sB2[ch]);
+                    const float v = silu_fast(__uint_as_float(r[e]) + sB2[ch]);
                     gd = fmaf(v, sWg[ch], gd);
                     m[part * 32 + e] = v;
                 }
@@ -611,7 +608,7 @@ __global__ void __launch_bounds__(TC_THREADS_ALL, 1) embed_edge_tc_kernel(const 
             sGp[half * TP + e_row] = gd;
             tcg_fence_before();  // the accumulator reads above are ordered before the next tile's first MMA (via a_full)
             named_bar_sync(1, TC_GEN_THREADS);
-            const float gate = sigmoid_nr((sGp[e_row] + sGp[TP + e_row]) + p.bg) * sValid[e_row];
+            const float gate = sigmoid_fast((sGp[e_row] + sGp[TP + e_row]) + p.bg) * sValid[e_row];
             // sum over the tile's 16 residues j = the 16 lanes of a half-warp: transpose-reduce (each step a lane keeps
             // one half of its channels and receives the partner's sums for that half) -- 120 shuffles instead of 512
             const bool b3 = (lane & 8) != 0, b2 = (lane & 4) != 0, b1 = (lane & 2) != 0, b0 = (lane & 1) != 0;
