@@ -17,14 +17,13 @@ from __future__ import annotations
 
 import logging
 import os
-import pickle
 import sys
 import time
 from typing import Dict, Iterable, Optional, Tuple
 
 import numpy as np
 
-from . import native
+from . import dbindex, native
 from .engine import LocalEngine
 
 logger = logging.getLogger(__name__)
@@ -77,9 +76,8 @@ def read_database(db_name: str, device):
 
     if os.path.exists(db_name + ".pt"):
         key = (os.path.abspath(db_name + ".pt"), "pt")
-        with open(db_name + ".index", "rb") as targfile:
-            target_index = pickle.load(targfile)
-        lengths = np.asarray([len(t[2]) for t in target_index], dtype=np.int32)
+        # <db>.index: the reference's pickle, or its one-time converted flat layout when present (dbindex.py)
+        target_index, lengths = dbindex.load_index(db_name)
         if key in _RESIDENT:
             resident = _RESIDENT[key]
         else:
