@@ -11,6 +11,10 @@
   per-rank ``[nq,k]`` packed key lists are exchanged with a single NCCL all-gather (8 bytes per
   entry over NVLink) and merged on every rank by the same kernel.  The key exchange is the only
   collective on the path.
+* ``embed_partition`` / ``distributed_embed`` -- the step before the search under torchrun: the
+  structures of a batch are independent, so each rank embeds a contiguous slice (balanced by
+  sum of L^2, the embedder's cost) and ONE all-gather of the [n/world,128] fp32 embeddings
+  (512 B per structure) gives every rank the replicated query matrix the search takes.
 
 torch is used for device memory, streams and torch.distributed only.
 """
@@ -251,3 +255,52 @@ class DistributedEngine:
             native.merge_topk(self.device or 0, lists.data_ptr(), self.row_shards, self.q_groups * per, k, sc.data_ptr(),
                               ids.data_ptr(), stream=st.cuda_stream)
         return sc[:nq], ids[:nq]
+
+
+def embed_partition(lengths: Sequence[int], parts: int) -> List[Tuple[int, int]]:
+    """Contiguous slices [lo, hi) of a batch of structures, one per rank, balanced by sum of L^2 (the edge kernel's
+    cost is quadratic in the structure length; counts alone would leave the rank with the long chains behind)."""
+    if parts < 1:
+        raise ValueError("parts >= 1 required")
+    n = len(lengths)
+    cost = np.asarray(lengths, dtype=np.float64) ** 2
+    cum = np.concatenate([[0.0], np.cumsum(cost)])
+    total = cum[-1]
+    bounds = [0]
+    for p in range(1, parts):
+        # first index whose prefix cost reaches p/parts of the total; never before the previous boundary
+        b = int(np.searchsorted(cum, total * p / parts, side="left"))
+        bounds.append(min(n, max(b, bounds[-1])))
+    bounds.append(n)
+    return [(bounds[p], bounds[p + 1]) for p in range(parts)]
+
+
+def distributed_embed(structures: Sequence[np.ndarray], embed_fn: Callable, device=None):
+    """Under torch.distributed (same `structures` on every rank): rank r embeds its slice with
+    ``embed_fn(list_of_coords) -> [m,128]`` (torch tensor on `device`, or a numpy array), then one
+    ``all_gather_into_tensor`` of the padded [per,128] blocks; returns the full [n,128] torch tensor, identical on
+    every rank.  With one process it is just ``embed_fn(structures)``."""
+    import torch
+    import torch.distributed as dist
+
+    n = len(structures)
+    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    rank = dist.get_rank() if world > 1 else 0
+    lens = [int(np.asarray(c).reshape(-1, 3).shape[0]) for c in structures]
+    parts = embed_partition(lens, world)
+    lo, hi = parts[rank]
+    mine = embed_fn(list(structures[lo:hi])) if hi > lo else np.zeros((0, DIM), dtype=np.float32)
+    mine = torch.as_tensor(mine, dtype=torch.float32)
+    if device is not None:
+        mine = mine.to(device)
+    if world == 1:
+        return mine
+    per = max(h - l for l, h in parts)
+    block = torch.zeros((per, DIM), dtype=torch.float32, device=mine.device)
+    block[: hi - lo] = mine
+    gathered = torch.empty((world * per, DIM), dtype=torch.float32, device=mine.device)
+    dist.all_gather_into_tensor(gathered, block)  # the only collective of the embedding step: 512 B per structure
+    out = torch.empty((n, DIM), dtype=torch.float32, device=mine.device)
+    for r, (l, h) in enumerate(parts):
+        out[l:h] = gathered[r * per: r * per + (h - l)]
+    return out
