@@ -341,16 +341,16 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) embed_edge_kernel(const EdgeP
 // bf16 hi + lo parts and three products are accumulated in fp32 in TMEM:  hh.Wh + hl.Wh + hh.Wl  (the dropped
 // hl.Wl term is ~2^-16 relative; measured on the golden set the embedding differs from the fp32 reference by
 // < 1e-6 relative, the same as the fp32 kernel).  Per 32-wide chunk of the hidden layer (two UMMA k-steps):
-//   * all 256 threads generate the chunk's activations (thread = pair row x 16 hidden units), split them and store
+//   * warps 0..7 (generators; thread = pair row x 16 hidden units) compute the chunk's activations, split them and store
 //     the hi / lo A operand images straight into shared memory in the canonical K-major no-swizzle core-matrix layout
-//     (8 rows x 16 B core matrices, LBO 128 B, SBO 512 B), then fence.proxy.async + __syncthreads;
-//   * thread 0 waits for the chunk's W2 image (hi | lo, 32 KB, one 1-D bulk copy, three stages, prefetched one chunk
-//     ahead -- the images are identical for every tile, so the copy stream simply cycles over the 17 chunks),
-//     issues 2 x 3 tcgen05.mma.kind::f16 M128 x N256 x K16 and commits to the stage's mbarrier;
+//     (8 rows x 16 B core matrices, LBO 128 B, SBO 512 B), then fence.proxy.async and ONE elected mbarrier arrive per warp;
+//   * warp 8 (one thread) streams the chunk's W2 image (hi | lo, 32 KB, one 1-D bulk copy; the images are identical for
+//     every tile, so the copy stream simply cycles over the 17 chunks), waits for both operands, issues 2 x 3
+//     tcgen05.mma.kind::f16 M128 x N256 x K16 and commits to the stage's mbarrier;
 //   * three stages of each operand: the generators run up to two chunks ahead of the MMAs.
-// Epilogue (all 8 warps; warp = TMEM lane quadrant x channel half): tcgen05.ld of the 128 x 256 fp32 accumulators,
-// m = SiLU(acc + b2) kept in registers (128 per thread), gate dot product thread-local + one shared-memory
-// exchange between the two channel halves, sum over the tile's 16 residues j by 16-lane shuffles.
+// Epilogue (the 8 generator warps; warp = TMEM lane quadrant x channel half): tcgen05.ld of the 128 x 256 fp32
+// accumulators, m = SiLU(acc + b2) kept in registers (128 per thread), gate dot product thread-local + one shared-memory
+// exchange between the two channel halves, sum over the tile's 16 residues j by a transpose-reduce over 16 lanes.
 constexpr int KT = 32;                 // hidden units per chunk
 constexpr int EHT = 544;               // 514 padded to 17 x 32 (pads: h = SiLU(0) = 0 and zero weights)
 constexpr int NCH_T = EHT / KT;        // 17
