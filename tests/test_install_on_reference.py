@@ -68,3 +68,98 @@ def test_embedder_accepts_the_reference_networks_state_dict(ref_module):
         for name, (_suffix, shape) in native.EGNN_KEYS.items():
             assert layer[name].shape == shape
     assert b200_embed.positional_table_from_state_dict(sd).shape == (3000, 128)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Driver-level parity: the reference's OWN dbsearch() run twice on the same .pt database -- untouched, and with
+# install() applied (the CUDA engine replaced by the CPU oracle, since this container has no GPU).  Everything around
+# the replaced callables (query embedding, index lookups, metadata retrieval, result dicts) is the reference's code.
+# ------------------------------------------------------------------------------------------------------------------
+class _OraclePtEngine:
+    """engine.LocalEngine look-alike for the .pt flavour: raw rows + lengths in, cosine * mask -> topk by the oracle."""
+
+    def __init__(self, n_rows, devices=None, normalise_rows=False, keep_bf16=False, has_lengths=False):
+        import numpy as np
+
+        assert normalise_rows and has_lengths, "the .pt flavour uploads raw rows and lengths"
+        self.n_rows = n_rows
+        self.rows = np.zeros((n_rows, 128), np.float32)
+        self.lens = np.zeros(n_rows, np.int32)
+
+    def upload(self, row0, rows, lengths=None):
+        self.rows[row0:row0 + len(rows)] = rows
+        self.lens[row0:row0 + len(rows)] = lengths
+
+    def finalize(self):
+        pass
+
+    def close(self):
+        pass
+
+    def search(self, q, k, qlen=None, mincov=0.0, qnorm=None, mode=None, kprime=0):
+        import numpy as np
+        import torch
+
+        from merizo_search_b200 import native
+        from oracle import foldclass_oracle as orc
+
+        assert qnorm == native.QNORM_COSINE and q.shape[0] == 1
+        s, i, _ = orc.search_torch_flavour(torch.from_numpy(self.rows), torch.from_numpy(self.lens.astype(np.float32)),
+                                           torch.from_numpy(q[0]), int(qlen[0]), float(mincov), int(k))
+        return s.numpy()[None], i.numpy()[None]
+
+
+def test_reference_dbsearch_driver_gives_the_same_hits_with_the_spliced_path(ref_module, tmp_path, monkeypatch):
+    import json
+    import pickle
+
+    import numpy as np
+    import torch
+
+    from merizo_search_b200 import dbsearch as b200
+    from merizo_search_b200 import synth
+
+    torch.manual_seed(3)
+    net = ref_module.FoldClassNet(128).eval()
+    with torch.no_grad():  # give the random-init network O(1) weights so that embeddings differ between structures
+        for prm in net.parameters():
+            prm.mul_(300.0)
+    lens = [30, 45, 25, 60, 33, 28, 51, 40, 37, 26, 48, 55]
+    chains = synth.synthetic_chains(lens, seed=17)
+    seqs = ["A" * L for L in lens]
+    base = str(tmp_path / "mini")
+    with torch.no_grad():
+        rows = torch.cat([net(torch.from_numpy(c).unsqueeze(0)) for c in chains], dim=0)
+    torch.save(rows, base + ".pt")
+    with open(base + ".index", "wb") as fh:
+        pickle.dump([(f"/x/dom{i:03d}.pdb", c, s) for i, (c, s) in enumerate(zip(chains, seqs))], fh)
+    metas = [json.dumps({"cath": f"1.10.{i}.1"}) for i in range(len(lens))]
+    off, idx = 0, []
+    with open(base + ".metadata", "wb") as fh:
+        for m in metas:
+            fh.write(m.encode("ascii"))
+            idx.append((off, off + len(m)))
+            off += len(m)
+    np.asarray(idx, dtype=np.int64).tofile(base + ".metadata.index")
+    query = {"name": "/q/query.pdb", "coords": (chains[3] + 0.05).astype(np.float32), "seq": "A" * lens[3]}
+
+    def run():
+        target = ref_module.read_database(base, torch.device("cpu"))
+        return ref_module.dbsearch(dict(query), target, str(tmp_path), net, 5, 0.7, 0.5, 0.5, False, torch.device("cpu"),
+                                   inputs_are_ca=True, skip_tmalign=True)
+
+    want, _ = run()                                   # the untouched reference
+    monkeypatch.setattr(b200, "LocalEngine", _OraclePtEngine)
+    b200._RESIDENT.clear()
+    b200.install(ref_module)
+    got, _ = run()                                    # the same driver, hot path spliced
+    b200._RESIDENT.clear()
+    assert len(want) >= 2 and list(got.keys()) == list(want.keys())
+    for key in want:
+        w, g = want[key], got[key]
+        assert set(g) == set(w)
+        for field in ("query", "target", "q_len", "t_len", "metadata", "tmalign_output", "dom_str"):
+            assert g[field] == w[field], field
+        assert int(g["dbindex"]) == int(w["dbindex"])
+        assert abs(float(g["score"]) - float(w["score"])) <= 1e-6
+        assert "{:.4f}".format(g["score"]) == "{:.4f}".format(w["score"])  # what the TSV writer prints
