@@ -163,3 +163,40 @@ def test_reference_dbsearch_driver_gives_the_same_hits_with_the_spliced_path(ref
         assert int(g["dbindex"]) == int(w["dbindex"])
         assert abs(float(g["score"]) - float(w["score"])) <= 1e-6
         assert "{:.4f}".format(g["score"]) == "{:.4f}".format(w["score"])  # what the TSV writer prints
+
+
+def test_record_readers_on_the_bundled_ted_slice_fixtures(tmp_path):
+    """The real on-disk layout (examples/database/ted100_9606_small: names + offset indices are bundled, the .db payloads
+    are missing large blobs): 33-byte name records, int64 [N,2] (start,end) tables, 12 bytes of coordinates per residue."""
+    import json
+
+    import numpy as np
+
+    from merizo_search_b200 import faiss_driver
+
+    src = "/root/reference/examples/database/ted100_9606_small"
+    if not os.path.isdir(src):
+        pytest.skip("bundled TED slice not present")
+    info = json.load(open(os.path.join(src, "ted100_9606_small.json")))
+    n = int(info["DB_SIZE"])
+    assert n == 66943 and int(info["DB_DIM"]) == 128
+    seq_idx = np.fromfile(os.path.join(src, info["sif"]), dtype=np.int64).reshape(-1, 2)
+    ca_idx = np.fromfile(os.path.join(src, info["cif"]), dtype=np.int64).reshape(-1, 2)
+    assert seq_idx.shape == (n, 2) and ca_idx.shape == (n, 2)
+    lens = seq_idx[:, 1] - seq_idx[:, 0]
+    assert lens.min() == 25 and lens.max() == 683                      # SURVEY.md §8c
+    assert np.array_equal(ca_idx[:, 1] - ca_idx[:, 0], 12 * lens)      # float32 [L,3] per domain
+    assert np.array_equal(seq_idx[1:, 0], seq_idx[:-1, 1])             # records are contiguous
+    # the readers need the payload files to exist: stand-ins of the right size, real names + indices
+    for key in ("db_names_f", "sif", "cif", "mif"):
+        os.symlink(os.path.join(src, info[key]), tmp_path / info[key])
+    rng = np.random.default_rng(0)
+    seq_payload = rng.choice(np.frombuffer(b"ACDEFGHIKLMNPQRSTVWY", dtype=np.uint8), size=int(seq_idx[-1, 1]))
+    seq_payload.tofile(tmp_path / info["sdf"])
+    rec = faiss_driver.RecordFiles(str(tmp_path), info)
+    ids = np.array([0, 1, 12345, n - 1])
+    names = rec.names(ids)
+    assert all(nm.startswith("AF-") and "TED" in nm and " " not in nm for nm in names), names
+    seqs = rec.sequences(ids)
+    assert [len(s) for s in seqs] == lens[ids].tolist()
+    assert seqs[2] == bytes(seq_payload[seq_idx[12345, 0]:seq_idx[12345, 1]]).decode("ascii")
