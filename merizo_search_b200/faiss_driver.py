@@ -75,6 +75,12 @@ class RecordFiles:
         se = np.asarray(idx[np.asarray(ids, dtype=np.int64)])  # one fancy-indexed read for all hits
         return [dat[int(s):int(e)] for s, e in se]
 
+    def lengths(self, ids) -> np.ndarray:
+        """Domain lengths of the hits straight from the (start,end) table: no payload bytes are touched."""
+        idx, _ = self._pair("sif", "sdf")
+        se = np.asarray(idx[np.asarray(ids, dtype=np.int64)])
+        return (se[:, 1] - se[:, 0]).astype(np.int64)
+
     def sequences(self, ids) -> List[str]:
         return [bytes(b).decode("ascii") for b in self._ranges("sif", "sdf", ids)]
 
@@ -181,10 +187,12 @@ def dbsearch_faiss(queries: list, target_dict: dict, tmp: str, network, topk: in
     rec = RecordFiles(db_dir, dbinfo)
     logger.info("Retrieve domain hits...")
     hit_ids = rec.names(hit_indices)
-    hit_seqs = rec.sequences(hit_indices)
+    # sequences and coordinates are only needed to write the PDB files TM-align reads; without TM-align the target lengths
+    # come from the offset table alone (3.3 M hits at 65,536 queries x k=50: no per-hit payload reads)
+    hit_seqs = rec.sequences(hit_indices) if not skip_tmalign else None
     hit_coords = rec.coords(hit_indices) if not skip_tmalign else None
     hit_metadata = rec.metadata(hit_indices) if rec.has_metadata() else ["{ }"] * n_hits
-    hit_lengths = [len(s) for s in hit_seqs]
+    hit_lengths = rec.lengths(hit_indices).tolist()
 
     n_q = int(query_indices.max()) + 1
     results = [dict() for _ in range(n_q)]

@@ -78,6 +78,7 @@ def test_record_files_vectorised_readers(tiny_faiss_db):
     ids = np.array([49, 0, 7, 7, 23])
     assert rec.names(ids) == [names[i] for i in ids]
     assert rec.sequences(ids) == [seqs[i] for i in ids]
+    assert rec.lengths(ids).tolist() == [len(seqs[i]) for i in ids]  # from the offset table alone
     assert rec.metadata(ids) == [metas[i] for i in ids]
     for got, i in zip(rec.coords(ids), ids):
         np.testing.assert_array_equal(got, coords[i])
