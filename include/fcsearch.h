@@ -88,6 +88,11 @@ int fcs_db_create(int device, int64_t n_rows, int dim /* must be 128 */, int64_t
 /* Copy rows [row0, row0+n) from HOST memory (pageable is fine: staged through pinned
  * buffers).  lengths (int32, one per row) is required iff FCS_DB_HAS_LENGTHS. */
 int fcs_db_upload(fcs_db* db, int64_t row0, int64_t n, const float* host_rows, const int32_t* host_lengths);
+/* Same, straight from a FILE of headerless fp32 rows (the faiss flavour's `*_raw_128d_norm.db`,
+ * dbutil.py:28-30): rows [row0, row0+n) are read from byte `file_offset` on with positional reads
+ * into the pinned staging buffers -- no intermediate copy, no page faults on a mapping.  Not for
+ * databases with domain lengths. */
+int fcs_db_upload_file(fcs_db* db, int64_t row0, int64_t n, const char* path, int64_t file_offset);
 /* Same, from DEVICE memory on the handle's device (synthetic DBs, torch CUDA tensors). */
 int fcs_db_upload_device(fcs_db* db, int64_t row0, int64_t n, const float* dev_rows, const int32_t* dev_lengths);
 /* Normalise rows (if asked), build the bf16 copy (if asked), allocate search scratch. */
@@ -107,17 +112,48 @@ int fcs_db_destroy(fcs_db* db);
 int fcs_search(fcs_db* db, const float* q, int nq, const int32_t* qlen, float mincov, int k, int qnorm,
                int mode, int kprime, float* out_scores, int64_t* out_ids);
 /* Same with DEVICE buffers, asynchronous on `stream` (a cudaStream_t; NULL = the
- * handle's own stream).  qlen stays a HOST array.  out_keys ([nq,k] uint64, optional)
- * receives the packed sort keys that fcs_merge_topk consumes. */
+ * handle's own stream): the call only enqueues work and never synchronises, so it can sit
+ * between an upstream kernel and a collective.  qlen stays a HOST array.  out_keys
+ * ([nq,k] uint64, optional) receives the packed sort keys that fcs_merge_topk consumes.
+ * Tensor-core searches queue the queries whose exactness certificate failed on the device and
+ * re-run up to FCS_ASYNC_FALLBACK_QUERIES of them on the exact scan inside the same
+ * enqueued work; a longer queue (pathological data: thousands of near-identical rows) is
+ * completed by fcs_search_finish. */
+#define FCS_ASYNC_FALLBACK_QUERIES 32
 int fcs_search_device(fcs_db* db, const float* q_dev, int nq, const int32_t* qlen, float mincov, int k,
                       int qnorm, int mode, int kprime, float* out_scores_dev, int64_t* out_ids_dev,
                       uint64_t* out_keys_dev, void* stream);
+/* Synchronises `stream` (NULL = the handle's own) and, if the last fcs_search_device queued more
+ * than FCS_ASYNC_FALLBACK_QUERIES queries for the exact scan, scans the rest into the same output
+ * buffers (which must still be valid) and waits.  *out_queued (optional) = length of that queue.
+ * Cheap when there is nothing to do; fcs_search does this itself. */
+int fcs_search_finish(fcs_db* db, void* stream, int* out_queued);
 
 /* cross-shard merge (replaces faiss.ResultHeap.add_result/finalize, dbsearch.py:224-245):
  *   keys_dev [n_lists][nq][k] packed keys from fcs_search_device of each shard (after the
  *   all-gather), -> the k best per query, decoded.  Asynchronous on `stream`. */
 int fcs_merge_topk(int device, const uint64_t* keys_dev, int n_lists, int nq, int k, float* out_scores_dev,
                    int64_t* out_ids_dev, void* stream);
+
+/* shard group: several row shards behind one handle, one host thread (replaces
+ * faiss.index_cpu_to_all_gpus + ResultHeap, dbsearch.py:228-245) -----------------------------------
+ * `devices[s]` is the GPU of shard s (an ordinal may repeat: several shards on one GPU).  Shard s
+ * holds rows [s*ceil(N/G), min(N,(s+1)*ceil(N/G))); ids are global.  upload / upload_file /
+ * finalize feed every shard from its own host thread; search replicates the queries, searches
+ * all shards concurrently, moves the per-shard key lists device-to-device (NVLink peer copies)
+ * to devices[0] and merges them there.  Same argument meaning and result contract as fcs_search. */
+typedef struct fcs_group fcs_group;
+int fcs_group_create(const int* devices, int n_shards, int64_t n_rows, int dim, uint32_t flags, fcs_group** out);
+int fcs_group_upload(fcs_group* g, int64_t row0, int64_t n, const float* host_rows, const int32_t* host_lengths);
+int fcs_group_upload_file(fcs_group* g, const char* path, int64_t file_offset, int64_t row0, int64_t n);
+int fcs_group_finalize(fcs_group* g);
+int fcs_group_search(fcs_group* g, const float* q, int nq, const int32_t* qlen, float mincov, int k, int qnorm,
+                     int mode, int kprime, float* out_scores, int64_t* out_ids);
+/* out_bounds: n_shards+1 row offsets; out_devices: n_shards ordinals (either may be NULL) */
+int fcs_group_get_info(const fcs_group* g, int* out_n_shards, int64_t* out_bounds, int* out_devices, int max_shards);
+int fcs_group_shard(fcs_group* g, int index, fcs_db** out); /* borrowed handle (timing, info) */
+int fcs_group_last_fallbacks(const fcs_group* g);           /* exact-scan fallbacks of the last search, all shards */
+int fcs_group_destroy(fcs_group* g);
 
 /* last_search_ms needs fcs_set_profiling(db, 1) (two event records per call; off by default because an event
  * between two scan kernels prevents their programmatic-dependent-launch overlap).  The TC path always times
@@ -128,6 +164,11 @@ int fcs_get_timing(const fcs_db* db, fcs_timing* out);
 /* Test hook (not part of the drop-in surface): the approximate bf16 tensor-core score of every
  * (query,row) pair, out_scores [nq, n_rows] HOST fp32; only for shards of <= 4096 rows. */
 int fcs_debug_tc_approx(fcs_db* db, const float* q, int nq, int qnorm, float* out_scores);
+/* Test hooks: the round plan of the tensor-core path for a shard of n_rows rows (7 int64 per round: tiles, first sample
+ * index, sample stride, complement size, round-0 flag, selection rank, partition flag; returns the number of rounds) and
+ * the database tile a round visits at position idx. */
+int fcs_debug_tc_plan(int64_t n_rows, int kprime, int64_t* out_rounds, int max_rounds);
+int64_t fcs_debug_tc_tile_of(int64_t j0, int64_t stride, int64_t comp_t, int64_t idx);
 
 #ifdef __cplusplus
 }

@@ -20,7 +20,7 @@ INCLUDE = os.path.join(os.path.dirname(PKG_DIR), "include")
 LIB_PATH = os.path.join(PKG_DIR, "libfcsearch.so")
 STAMP_PATH = os.path.join(PKG_DIR, ".libfcsearch.stamp")
 
-SOURCES = ["fcs_api.cu", "fcs_gemv.cu", "fcs_loader.cu", "fcs_merge.cu", "fcs_tc.cu", "fcs_embed.cu"]
+SOURCES = ["fcs_api.cu", "fcs_group.cu", "fcs_gemv.cu", "fcs_loader.cu", "fcs_merge.cu", "fcs_tc.cu", "fcs_embed.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",

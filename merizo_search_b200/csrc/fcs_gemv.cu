@@ -73,6 +73,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemv_topk_kernel(const GemvParams
     const int lane = tid & 31;
     const int k = p.k;
     const int64_t n_chunks = (p.n_rows + STAGE_ROWS - 1) / STAGE_ROWS;
+    int nq = p.nq;
+    if (p.nq_dev) {
+        // indirect launch: the queue length was written by a predecessor on the stream.  Every thread waits for it
+        // here (the producer may not prefetch before the CTA knows whether it has work: a CTA must not exit with
+        // bulk copies in flight).
+        pdl_wait();
+        const unsigned total = *reinterpret_cast<const volatile unsigned*>(p.nq_dev);
+        const int rem = total > unsigned(p.nq_off) ? int(total - unsigned(p.nq_off)) : 0;
+        nq = rem < NQ ? rem : NQ;
+        if (nq == 0) return;
+    }
 
     WarpTopK<KPL> tk[NQ];
 #pragma unroll
@@ -113,7 +124,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemv_topk_kernel(const GemvParams
         // query normalisation fused here (dbsearch.py:78 cosine eps 1e-8 / dbsearch.py:304 F.normalize eps 1e-12)
         if (warp < NQ) {
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (warp < p.nq) v = reinterpret_cast<const float4*>(p.q + size_t(warp) * DIM)[lane];
+            if (warp < nq) v = reinterpret_cast<const float4*>(p.q + size_t(warp) * DIM)[lane];
             if (p.qnorm != FCS_QNORM_NONE) {
                 float ss = v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
 #pragma unroll
@@ -130,7 +141,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemv_topk_kernel(const GemvParams
 #pragma unroll
         for (int q = 0; q < NQ; ++q) {
             ub[q] = ~0ull;
-            if (p.bounded && q < p.nq) ub[q] = p.out_keys[size_t(q) * p.out_stride + p.out_off - 1];
+            if (p.bounded && q < nq) ub[q] = p.out_keys[size_t(p.out_index ? p.out_index[q] : q) * p.out_stride + p.out_off - 1];
         }
         // this lane's row inside the stage, and its 8 swizzled chunk offsets (bytes)
         const uint8_t* my_row = ring + warp * STAGE_BYTES + lane * ROW_BYTES;
@@ -210,7 +221,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemv_topk_kernel(const GemvParams
     __threadfence();
     const int G = int(gridDim.x);
     for (int q = 0; q < NQ; ++q) {
-        if (q >= p.nq) break;
+        if (q >= nq) break;
         const uint64_t* src = p.scratch + size_t(q) * G * k;
         uint64_t* mine = lists + size_t(warp) * k;  // one smem list per warp (12 warps incl. the producer's)
         {
@@ -248,7 +259,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemv_topk_kernel(const GemvParams
                 __syncthreads();
             }
         }
-        const size_t base = size_t(q) * p.out_stride + p.out_off;
+        const size_t base = size_t(p.out_index ? p.out_index[q] : q) * p.out_stride + p.out_off;
         for (int r = tid; r < k; r += NTHREADS) {
             const uint64_t key = lists[r];
             p.out_keys[base + r] = key;
@@ -298,6 +309,7 @@ cudaError_t gemv_configure() {
 
 cudaError_t gemv_launch(const GemvParams& p, int sm_count, cudaStream_t stream) {
     if (p.nq < 1 || p.nq > GEMV_MAX_NQ || p.k < 1 || p.k > GEMV_MAX_K || p.n_rows < 1) return cudaErrorInvalidValue;
+    if (p.nq_dev && p.nq != GEMV_MAX_NQ) return cudaErrorInvalidValue;  // indirect launches use the 8-query instantiation
     const int64_t n_chunks = (p.n_rows + GEMV_STAGE_ROWS - 1) / GEMV_STAGE_ROWS;
     const int grid = int(n_chunks < sm_count ? n_chunks : sm_count);
     const int nqt = p.nq == 1 ? 1 : (p.nq == 2 ? 2 : (p.nq <= 4 ? 4 : 8));

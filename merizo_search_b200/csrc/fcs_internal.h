@@ -37,6 +37,12 @@ struct GemvParams {
     uint64_t* out_keys;     // [nq][out_stride]
     float* out_scores;      // [nq][out_stride] or nullptr
     int64_t* out_ids;       // [nq][out_stride] or nullptr
+    // Indirect launch (the tensor-core path's device-side fallback queue): the number of queries is read on the
+    // device, nq = clamp(*nq_dev - nq_off, 0, GEMV_MAX_NQ) -- a launch with nothing to do exits at once -- and
+    // query i writes output row out_index[i] instead of row i.
+    const unsigned* nq_dev; // nullptr = direct launch
+    int nq_off;
+    const int* out_index;   // [nq] output rows or nullptr
 };
 
 size_t gemv_scratch_bytes(int max_grid);

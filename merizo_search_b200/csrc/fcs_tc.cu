@@ -14,29 +14,40 @@
 //        * warp 0: TMA producer.  warps 1-4: one thread each issues tcgen05.mma.kind::f16, M128 x N128 x
 //          K16, 8 per (query tile, DB tile), one query tile per issuer (a single thread can only issue one
 //          MMA per ~75 cycles; two or more issuers reach the 64-cycle math rate, scripts/micro/
-//          umma_two_issuers.cu, and one issuer per tile keeps a slow epilogue from stalling the other tiles).  Measured on B200 (scripts/micro/umma_rate.cu): one tcgen05.mma costs
-//          >= 70 cycles whatever its N, so N=64 caps the tensor pipe at 46 % and N=128 reaches 90 %
-//          (N=256: 100 %); A from TMEM instead of shared memory changes nothing.  Accumulators: fp32 in
-//          TMEM, one 128-column buffer per query tile = all 512 columns; the epilogue of tile t drains
-//          its buffer while the MMAs of the other three tiles run.
+//          umma_two_issuers.cu).  Accumulators: fp32 in TMEM, one 128-column buffer per query tile = all
+//          512 columns; the epilogue of tile t drains its buffer while the MMAs of the other three run.
 //        * warps 5..20: epilogue, one THREAD PER QUERY (tcgen05.ld 32x32b: lane = accumulator row).
 //          Each thread reduces its scores 32 at a time with 3-input max, compares the group maximum
-//          with the query's current threshold and only on a hit scans the 8-column sub-groups and
-//          appends (score,row) keys to the query's candidate buffer in HBM (slots are reserved 8 at a
-//          time with one atomic; the first round, where every row qualifies, indexes by row instead).
-//        The threshold is a per-query constant during a launch; it is the k'-th best approximate
-//        score over the rows seen so far.  The DB is therefore swept in ROUNDS of geometrically
-//        growing size with a small selection kernel (tc_select_warp_kernel) in between, which keeps the
-//        number of appends at about k' per round and the epilogue on its fast path.
-//   K4  tc_rescore_kernel -- one warp per query gathers the k' candidate rows (fp32), recomputes the
-//        inner products exactly, keeps the k best, and checks the exactness certificate
-//        (k-th exact score) > (k'-th approximate score) + eps, eps = rigorous bf16 rounding bound.
-//        Queries that fail it (or overflowed their buffer) are re-run on the exact fp32 scan (K2).
+//          with the query's threshold and only on a hit scans the 8-column sub-groups and appends
+//          (score,row) keys to the query's candidate buffer in HBM (slots reserved with one atomic).
+//
+//   The threshold is a per-query constant during a launch.  It comes from a SAMPLE of the database, not from a
+//   running top-k': the rows above the m-th best score of a sample of S rows number about m*N/S in the whole
+//   shard, so a small m and a large N/S give a good threshold after very little work.  A search is therefore
+//     round 0   32 tiles spread evenly over the shard (4096 rows), every score recorded (slot = sample row);
+//     round i   a larger, nested strided sample, threshold = rank-m_i score of what has been seen
+//               (m_i chosen so that about C1 = 1024 rows of the round qualify);
+//     sweep     every tile that was not sampled, threshold = rank-24 score of the last sample (about
+//               max(3k', 512) rows qualify) -- 95 % of the rows, at a hit density the epilogue absorbs;
+//   each followed by tc_select_kernel (one block per query, radix select on the order-preserving score word).
+//   Every tile is multiplied exactly once.  cfg3 (10 M rows) takes 3 GEMM launches instead of 9.
+//
+//   K4  tc_rescore_kernel -- one warp per query.  Phase A: the k' best approximate candidates are gathered
+//        (fp32 rows), their inner products recomputed exactly, the k best kept; certificate
+//        s_k(exact) > t' + eps with t' = the k'-th approximate score (every non-candidate has an approximate
+//        score <= t').  Phase B, only when A fails: ALL rows above the sweep threshold (they are still in the
+//        buffer, behind the k' best) are rescored; certificate with t' = the sweep threshold, which lies far
+//        below the k-th score.  eps = |q|*max|r - bf16(r)| + |q - bf16(q)|*max|bf16(r)| + fp32 accumulation
+//        slack: a rigorous Cauchy-Schwarz bound from the measured rounding errors of both operands.
+//        Queries that fail both (or lost candidates to an overflowing buffer) are queued ON THE DEVICE for
+//        the exact fp32 scan (K2, launched with a device-side count): no host round trip anywhere in a search.
 #include <cuda_bf16.h>
 
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <string>
+#include <vector>
 
 #include "fcs_common.cuh"
 #include "fcs_internal.h"
@@ -58,8 +69,10 @@ constexpr int TC_RES_MAX = 16;                    // candidate slots reserved pe
 constexpr int TC_MMA_WARPS = 4;                   // MMA-issuing warps (one thread each), one query tile apiece
 constexpr int TC_THREADS = (1 + TC_MMA_WARPS + 16) * 32;  // producer + MMA issuers + 16 epilogue warps
 constexpr int TC_CAP = 4096;                     // candidate slots per query
+constexpr int TC_R0_TILES = TC_CAP / TC_N;       // round 0 records every score of 32 tiles
 constexpr int TC_SMEM = TC_QT * A_TILE_BYTES + TC_STAGES * B_TILE_BYTES + 32 * 8 + 16;
 constexpr int TC_MAX_KPRIME = 512;
+constexpr int TC_MAX_RANK = 1024;                // largest selection rank used for a threshold
 
 // Operand image layout (K-major, SWIZZLE_NONE "interleave" canonical layout, cute mma_sm100_desc):
 // 8x8 core matrices of 128 contiguous bytes (8 rows x 16 B); the 16 core matrices along K of one
@@ -109,29 +122,45 @@ __device__ __forceinline__ float max3(float a, float b, float c) {
     asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
     return d;
 }
+__device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
 // ------------------------------------------------------------------------------------------------
-// one-time: fp32 (row-swizzled) rows -> bf16 operand images; also max row norm (for the certificate)
+// one-time: fp32 (row-swizzled) rows -> bf16 operand images.  Also, for the exactness certificate, the largest
+// norm of a ROUNDED row and the largest norm of a row's rounding error over the shard (stats[0], stats[1]:
+// squared, as float bits -- non-negative floats order like unsigned integers).
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) tc_build_bimg_kernel(const float* __restrict__ rows, int64_t n_rows, int64_t n_tiles,
-                                                            uint8_t* __restrict__ b_img, unsigned* __restrict__ max_norm2_bits) {
+                                                            uint8_t* __restrict__ b_img, unsigned* __restrict__ stats) {
     const int64_t total = n_tiles * TC_N * 16;  // one thread per (row, 8-element k-chunk)
     const int64_t stride = int64_t(gridDim.x) * blockDim.x;
     for (int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; t < total; t += stride) {
         const int k8 = int(t & 15);
         const int64_t row = t >> 4;
-        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+        float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         if (row < n_rows) {
             const float4* src = reinterpret_cast<const float4*>(rows + row * DIM);
-            a = src[swz_chunk(2 * k8, row)];
-            b = src[swz_chunk(2 * k8 + 1, row)];
+            const float4 a = src[swz_chunk(2 * k8, row)];
+            const float4 b = src[swz_chunk(2 * k8 + 1, row)];
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
         }
-        float ss = a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w + b.x * b.x + b.y * b.y + b.z * b.z + b.w * b.w;
+        float ss = 0.f, dd = 0.f;
 #pragma unroll
-        for (int o = 8; o >= 1; o >>= 1) ss += __shfl_xor_sync(FULL, ss, o);  // 16 threads = one row
-        if (k8 == 0) atomicMax(max_norm2_bits, __float_as_uint(ss));          // ss >= 0: uint order == float order
-        __nv_bfloat162 p0 = __floats2bfloat162_rn(a.x, a.y), p1 = __floats2bfloat162_rn(a.z, a.w);
-        __nv_bfloat162 p2 = __floats2bfloat162_rn(b.x, b.y), p3 = __floats2bfloat162_rn(b.z, b.w);
+        for (int i = 0; i < 8; ++i) {
+            const float r = bf16_round(v[i]);
+            ss = fmaf(r, r, ss);
+            dd = fmaf(v[i] - r, v[i] - r, dd);
+        }
+#pragma unroll
+        for (int o = 8; o >= 1; o >>= 1) {  // 16 threads = one row
+            ss += __shfl_xor_sync(FULL, ss, o);
+            dd += __shfl_xor_sync(FULL, dd, o);
+        }
+        if (k8 == 0) {
+            atomicMax(stats + 0, __float_as_uint(ss));
+            atomicMax(stats + 1, __float_as_uint(dd));
+        }
+        __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0], v[1]), p1 = __floats2bfloat162_rn(v[2], v[3]);
+        __nv_bfloat162 p2 = __floats2bfloat162_rn(v[4], v[5]), p3 = __floats2bfloat162_rn(v[6], v[7]);
         uint4 o;
         o.x = *reinterpret_cast<uint32_t*>(&p0); o.y = *reinterpret_cast<uint32_t*>(&p1);
         o.z = *reinterpret_cast<uint32_t*>(&p2); o.w = *reinterpret_cast<uint32_t*>(&p3);
@@ -142,36 +171,62 @@ __global__ void __launch_bounds__(256) tc_build_bimg_kernel(const float* __restr
 }
 
 // ------------------------------------------------------------------------------------------------
-// per search: normalise queries, write fp32 copy + bf16 operand images, reset per-query state
+// per search: normalise queries, write fp32 copy + bf16 operand images, per-query certificate slack,
+// reset per-query state
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) tc_prep_kernel(const float* __restrict__ q_raw, int nq, int nq_pad, int qnorm,
-                                                      float* __restrict__ qn, uint8_t* __restrict__ a_img,
-                                                      float* __restrict__ thr, unsigned* __restrict__ cnt,
-                                                      unsigned* __restrict__ flags, float* __restrict__ q_norm,
-                                                      unsigned* __restrict__ n_flagged, unsigned first_round_rows) {
+struct TcPrepParams {
+    const float* q_raw;
+    int nq, nq_pad, qnorm;
+    float* qn;
+    uint8_t* a_img;
+    float* thr;
+    float* thr_sel;
+    unsigned* cnt;
+    unsigned* sel_cnt;
+    unsigned* flags;
+    float* eps;
+    unsigned* n_flagged;
+    unsigned first_round_slots;
+    float max_rhat;   // max |bf16(row)|
+    float max_dr;     // max |row - bf16(row)|
+};
+
+__global__ void __launch_bounds__(128) tc_prep_kernel(const TcPrepParams p) {
     const int lane = threadIdx.x & 31;
     const int q = blockIdx.x * 4 + (threadIdx.x >> 5);
-    if (q == 0 && lane == 0) *n_flagged = 0u;
-    if (q >= nq_pad) return;
+    if (q == 0 && lane == 0) *p.n_flagged = 0u;
+    if (q >= p.nq_pad) return;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    float nrm = 0.f;
-    if (q < nq) {
-        v = reinterpret_cast<const float4*>(q_raw + size_t(q) * DIM)[lane];
+    if (q < p.nq) {
+        v = reinterpret_cast<const float4*>(p.q_raw + size_t(q) * DIM)[lane];
         float ss = v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
 #pragma unroll
         for (int o = 16; o >= 1; o >>= 1) ss += __shfl_xor_sync(FULL, ss, o);
-        nrm = sqrtf(ss);
-        if (qnorm != FCS_QNORM_NONE) {
-            const float d = fmaxf(nrm, (qnorm == FCS_QNORM_COSINE) ? 1e-8f : 1e-12f);
+        if (p.qnorm != FCS_QNORM_NONE) {
+            const float d = fmaxf(sqrtf(ss), (p.qnorm == FCS_QNORM_COSINE) ? 1e-8f : 1e-12f);
             v.x = v.x / d; v.y = v.y / d; v.z = v.z / d; v.w = v.w / d;
-            nrm = nrm / d;
         }
-        reinterpret_cast<float4*>(qn + size_t(q) * DIM)[lane] = v;
+        reinterpret_cast<float4*>(p.qn + size_t(q) * DIM)[lane] = v;
+        // |q| and |q - bf16(q)| of the query as it is multiplied
+        const float ex = v.x - bf16_round(v.x), ey = v.y - bf16_round(v.y), ez = v.z - bf16_round(v.z), ew = v.w - bf16_round(v.w);
+        float qq = v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+        float dq = ex * ex + ey * ey + ez * ez + ew * ew;
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) {
+            qq += __shfl_xor_sync(FULL, qq, o);
+            dq += __shfl_xor_sync(FULL, dq, o);
+        }
         if (lane == 0) {
-            thr[q] = -INFINITY;
-            cnt[q] = first_round_rows;  // the first round indexes its candidates by row
-            flags[q] = 0u;
-            q_norm[q] = nrm;
+            const float nq_ = sqrtf(qq), ndq = sqrtf(dq);
+            // q.r - q^.r^ = q.(r - r^) + (q - q^).r^  =>  |error| <= |q| max|r - r^| + |q - q^| max|r^|;
+            // + fp32 accumulation of 128 exact bf16 products in the tensor core (3e-5 |q||r| is generous)
+            // + the rounding of the fp32 rescore itself
+            p.eps[q] = 1.002f * (nq_ * p.max_dr + ndq * p.max_rhat) + 3.2e-5f * nq_ * p.max_rhat;
+            p.thr[q] = -INFINITY;
+            p.thr_sel[q] = -INFINITY;
+            p.cnt[q] = p.first_round_slots;  // round 0 indexes its candidates by sample row
+            p.sel_cnt[q] = 0u;
+            p.flags[q] = 0u;
         }
     }
     __nv_bfloat162 p0 = __floats2bfloat162_rn(v.x, v.y), p1 = __floats2bfloat162_rn(v.z, v.w);
@@ -179,7 +234,7 @@ __global__ void __launch_bounds__(128) tc_prep_kernel(const float* __restrict__ 
     o.x = *reinterpret_cast<uint32_t*>(&p0);
     o.y = *reinterpret_cast<uint32_t*>(&p1);
     const int tile = q / TC_M, m = q % TC_M;
-    *reinterpret_cast<uint2*>(a_img + size_t(tile) * A_TILE_BYTES + image_offset(m, lane >> 1) + (lane & 1) * 8) = o;
+    *reinterpret_cast<uint2*>(p.a_img + size_t(tile) * A_TILE_BYTES + image_offset(m, lane >> 1) + (lane & 1) * 8) = o;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -187,18 +242,32 @@ __global__ void __launch_bounds__(128) tc_prep_kernel(const float* __restrict__ 
 // ------------------------------------------------------------------------------------------------
 struct TcGemmParams {
     const uint8_t* a_img;  // [n_qgroups*4][32 KB]
-    const uint8_t* b_img;  // [n_tiles][16 KB]
+    const uint8_t* b_img;  // [n_tiles][32 KB]
     int64_t n_rows;
     int nq;
     int n_qgroups;
-    int64_t tile0, tile1;  // DB tiles of this round
+    // the DB tiles of this round, enumerated by idx in [0, n_idx):
+    //   sample round      (comp_T == 0): tile = (j0 + idx) * stride
+    //   complement sweep  (comp_T  > 0): every tile except the sampled ones {j * stride : j < comp_T}
+    int64_t n_idx, j0, stride, comp_T;
     const float* thr;      // [nq] approximate-score threshold (strict >)
     unsigned* cnt;         // [nq] append counters
-    uint64_t* cand;        // [nq][TC_CAP] approximate keys (score, LOCAL row); 0 = unused reserved slot
-    int first_round;       // thresholds are all -inf and tile0 == 0: slot = row, no atomics
+    uint64_t* cand;        // [nq][TC_CAP] approximate keys (score, LOCAL row); 0 = unused slot
+    int first_round;       // round 0: thresholds are -inf, slot = idx * 128 + column, no atomics
     int trace_on;          // debug builds (FCS_TC_TRACE): record cycle stamps in this launch
     int res_block;         // slots reserved per atomic: small when many CTAs share a query group (unused slots are waste)
 };
+
+__device__ __forceinline__ int64_t tile_of(const TcGemmParams& p, int64_t idx) {
+    if (p.comp_T == 0) return (p.j0 + idx) * p.stride;
+    const int64_t gap = p.stride - 1;            // unsampled tiles per stride block
+    const int64_t body = p.comp_T * gap;
+    if (idx < body) {
+        const int64_t b = idx / gap;
+        return b * p.stride + 1 + (idx - b * gap);
+    }
+    return idx + p.comp_T;
+}
 
 #ifdef FCS_TC_TRACE
 // debug build only: cycle stamps of CTA 0 (MMA thread: row 0/1; epilogue warp of tile 0, quadrant 2: rows 2..4)
@@ -208,30 +277,25 @@ __device__ long long g_trace[5][256];
 #define TRACE(row, idx, cond) do { } while (0)
 #endif
 
-// Per-thread slot reservation: one atomic buys p.res_block slots of the query's buffer.
-struct SlotRes {
-    unsigned base = 0, used = ~0u;  // ~0u: nothing reserved yet
-};
-__device__ __forceinline__ void tc_append(const TcGemmParams& p, SlotRes& res, int q, float v, int64_t row) {
-    if (row >= p.n_rows) return;  // zero padding rows of the last DB tile
-    unsigned slot;
-    if (p.first_round) {
-        slot = unsigned(row);
-    } else {
-        if (res.used >= unsigned(p.res_block)) {
-            res.base = atomicAdd(p.cnt + q, unsigned(p.res_block));
-            res.used = 0;
-        }
-        slot = res.base + res.used++;
+// Per-thread slot reservation: one atomic buys res_block slots of the query's buffer (x = first slot, y = slots used;
+// y == ~0u: nothing reserved yet).  Deliberately NOT inlined: there are 32 call sites per 32-column part, and the
+// epilogue loop has to stay small enough for the instruction cache (an inlined append per column cost 3-5 k cycles
+// per hit in instruction-cache misses).
+__device__ __noinline__ uint2 tc_append(unsigned* cnt_q, uint64_t* cand_q, uint2 res, int res_block, uint64_t key) {
+    if (res.y >= unsigned(res_block)) {
+        res.x = atomicAdd(cnt_q, unsigned(res_block));
+        res.y = 0;
     }
-    if (slot < unsigned(TC_CAP)) p.cand[size_t(q) * TC_CAP + slot] = make_key(v, uint32_t(row));
+    const unsigned slot = res.x + res.y++;
+    if (slot < unsigned(TC_CAP)) cand_q[slot] = key;
+    return res;
 }
 // unused slots of the last reservation must read as empty
-__device__ __forceinline__ void tc_close_reservation(const TcGemmParams& p, SlotRes& res, int q) {
-    if (res.used == ~0u) return;  // this thread never appended
-    for (; res.used < unsigned(p.res_block); ++res.used) {
-        const unsigned slot = res.base + res.used;
-        if (slot < unsigned(TC_CAP)) p.cand[size_t(q) * TC_CAP + slot] = 0ull;
+__device__ __forceinline__ void tc_close_reservation(uint64_t* cand_q, uint2 res, int res_block) {
+    if (res.y == ~0u) return;  // this thread never appended
+    for (; res.y < unsigned(res_block); ++res.y) {
+        const unsigned slot = res.x + res.y;
+        if (slot < unsigned(TC_CAP)) cand_q[slot] = 0ull;
     }
 }
 
@@ -272,8 +336,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_filter_kernel(const TcG
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    // contiguous share of the linearised (query group, DB tile) steps of this round
-    const int64_t n_tiles = p.tile1 - p.tile0;
+    // contiguous share of the linearised (query group, tile index) steps of this round
+    const int64_t n_tiles = p.n_idx;
     const int64_t steps = int64_t(p.n_qgroups) * n_tiles;
     const int64_t s_begin = steps * blockIdx.x / gridDim.x;
     const int64_t s_end = steps * (blockIdx.x + 1) / gridDim.x;
@@ -296,10 +360,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_filter_kernel(const TcG
                     // only 2 stages (64 KB) can be in flight behind the one being consumed: pull tiles further
                     // ahead into L2 so the bulk copies below see L2 latency, not DRAM latency
                     if (j + TC_PREFETCH < seg_len)
-                        bulk_prefetch_l2(p.b_img + size_t(p.tile0 + ti + j + TC_PREFETCH) * B_TILE_BYTES, B_TILE_BYTES);
+                        bulk_prefetch_l2(p.b_img + size_t(tile_of(p, ti + j + TC_PREFETCH)) * B_TILE_BYTES, B_TILE_BYTES);
                     mbar_wait(&empty_b[st], ph ^ 1u);
                     mbar_arrive_expect_tx(&full_b[st], B_TILE_BYTES);
-                    bulk_g2s(sB + st * B_TILE_BYTES, p.b_img + size_t(p.tile0 + ti + j) * B_TILE_BYTES, B_TILE_BYTES, &full_b[st], pol_stream);
+                    bulk_g2s(sB + st * B_TILE_BYTES, p.b_img + size_t(tile_of(p, ti + j)) * B_TILE_BYTES, B_TILE_BYTES, &full_b[st], pol_stream);
                 }
                 s += seg_len;
             }
@@ -339,7 +403,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_filter_kernel(const TcG
                         tc_commit(&tmem_full[t]);
                         TRACE(1, it, blockIdx.x == 0 && t == 0);
                     }
-                    tc_commit(&empty_b[st]);  // B stage free once both issuers' MMAs have read it
+                    tc_commit(&empty_b[st]);  // B stage free once every issuer's MMAs have read it
                 }
                 tc_commit(a_empty);
                 s += seg_len;
@@ -357,83 +421,97 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_filter_kernel(const TcG
             const int64_t seg_len = (s_end - s < n_tiles - ti) ? (s_end - s) : (n_tiles - ti);
             const int q = int(qg) * TC_QGROUP + t * TC_M + quad * 32 + lane;
             const float thr = (q < p.nq) ? p.thr[q] : INFINITY;
-            SlotRes res;
+            const int qc = q < p.nq ? q : 0;
+            unsigned* cnt_q = p.cnt + qc;
+            uint64_t* cand_q = p.cand + size_t(qc) * TC_CAP;
+            uint2 res = make_uint2(0u, ~0u);
             for (int64_t j = 0; j < seg_len; ++j, ++it) {
                 const uint32_t tph = it & 1u;
                 mbar_wait(&tmem_full[t], tph);
                 tc_fence_after();
                 TRACE(2, it, blockIdx.x == 0 && warp == 5 && lane == 0);
-                const int64_t row_base = (p.tile0 + ti + j) * TC_N;
-                int pend_n = 0;
-                uint32_t pend_v0 = 0, pend_v1 = 0;
-                int64_t pend_r0 = 0, pend_r1 = 0;
-                // Fast path: 32 scores per tcgen05.ld, reduced with 3-input max, one compare against the
-                // threshold.  Slow path (some lane of the warp has a hit in an 8-column group): the group is
-                // re-read from TMEM into 8 fixed registers and handled by ONE compact, warp-uniform loop.  Keep
-                // it small: the first version unrolled an append site per column (~140 KB of SASS) and every hit
-                // ran through cold code -- instruction-cache misses cost 3-5 k cycles per append.
+                const int64_t row_base = tile_of(p, ti + j) * TC_N;
+                if (p.first_round) {
+                    // round 0: every score is recorded, slot = row of the sample (no threshold, no atomics)
+                    uint64_t* dst = cand_q + (ti + j) * TC_N;
 #pragma unroll 1
-                for (int part = 0; part < TC_N / 32; ++part) {
-                    const uint32_t taddr = tmem_base + lane_base + uint32_t(t * TC_N + part * 32);
-                    float m[4];
-                    {
+                    for (int part = 0; part < TC_N / 32; ++part) {
                         uint32_t r[32];
-                        tc_ld32(taddr, r);
+                        tc_ld32(tmem_base + lane_base + uint32_t(t * TC_N + part * 32), r);
                         tc_wait_ld();
+                        if (q < p.nq) {
 #pragma unroll
-                        for (int g = 0; g < 4; ++g) {
-                            const float* f = reinterpret_cast<const float*>(&r[g * 8]);
-                            m[g] = fmaxf(max3(f[0], f[1], f[2]), max3(max3(f[3], f[4], f[5]), f[6], f[7]));
+                            for (int c = 0; c < 32; c += 2) {
+                                const int64_t row = row_base + part * 32 + c;
+                                ulonglong2 kk;
+                                kk.x = row < p.n_rows ? make_key(__uint_as_float(r[c]), uint32_t(row)) : 0ull;
+                                kk.y = row + 1 < p.n_rows ? make_key(__uint_as_float(r[c + 1]), uint32_t(row + 1)) : 0ull;
+                                *reinterpret_cast<ulonglong2*>(dst + part * 32 + c) = kk;
+                            }
                         }
                     }
-                    const float mx = fmaxf(max3(m[0], m[1], m[2]), m[3]);
-                    if (__any_sync(FULL, p.first_round || mx > thr)) {  // rare once the threshold is warm
-                        unsigned wgm = 0;  // groups in which some lane has a hit (warp-uniform)
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tmem_empty[t]);
+                    continue;
+                }
+                // Two hits per tile are parked in registers and appended after the accumulator has been handed back to
+                // the MMA issuer (the append's atomic and store are off the critical path); further hits are appended
+                // at once.  A parked hit is (score bits, column of the tile).
+                int pend_n = 0;
+                uint32_t pend_v0 = 0, pend_v1 = 0;
+                int pend_c0 = 0, pend_c1 = 0;
+                // Fast path: 32 scores per tcgen05.ld, reduced with 3-input max, one compare against the threshold.
+                // Slow path (some lane of the warp has a hit among these 32 columns): the scores are still in
+                // registers; 32 predicated column checks, no second TMEM read.
+#pragma unroll 1
+                for (int part = 0; part < TC_N / 32; ++part) {
+                    uint32_t r[32];
+                    tc_ld32(tmem_base + lane_base + uint32_t(t * TC_N + part * 32), r);
+                    tc_wait_ld();
+                    const float* f = reinterpret_cast<const float*>(r);
+                    float mx;
+                    {
+                        float m[4];
 #pragma unroll
-                        for (int g = 0; g < 4; ++g) wgm |= __any_sync(FULL, p.first_round || m[g] > thr) ? (1u << g) : 0u;
-                        while (wgm) {
-                            const int g = __ffs(wgm) - 1;
-                            wgm &= wgm - 1;
-                            uint32_t v8[8];
-                            __syncwarp();  // lanes left the divergent append loop below at different times
-                            tc_ld8(taddr + uint32_t(g * 8), v8);
-                            tc_wait_ld();
-                            unsigned hits = 0;
+                        for (int g = 0; g < 4; ++g)
+                            m[g] = fmaxf(max3(f[g * 8], f[g * 8 + 1], f[g * 8 + 2]), max3(max3(f[g * 8 + 3], f[g * 8 + 4], f[g * 8 + 5]), f[g * 8 + 6], f[g * 8 + 7]));
+                        mx = fmaxf(max3(m[0], m[1], m[2]), m[3]);
+                    }
+                    if (__any_sync(FULL, mx > thr)) {  // rare once the threshold is warm
+                        if (mx > thr) {
 #pragma unroll
-                            for (int c = 0; c < 8; ++c) hits |= (p.first_round || __uint_as_float(v8[c]) > thr) ? (1u << c) : 0u;
-                            while (hits) {
-                                const int c = __ffs(hits) - 1;
-                                hits &= hits - 1;
-                                uint32_t bits = v8[0];
-#pragma unroll
-                                for (int cc = 1; cc < 8; ++cc) bits = (c == cc) ? v8[cc] : bits;
-                                const int64_t hit_row = row_base + part * 32 + g * 8 + c;
-                                // park up to two hits in registers: they are appended after the accumulator has been
-                                // handed back to the MMA issuer (the append's atomics/stores are off the critical path)
-                                if (pend_n == 0) {
-                                    pend_v0 = bits;
-                                    pend_r0 = hit_row;
-                                    pend_n = 1;
-                                } else if (pend_n == 1) {
-                                    pend_v1 = bits;
-                                    pend_r1 = hit_row;
-                                    pend_n = 2;
-                                } else {
-                                    tc_append(p, res, q, __uint_as_float(bits), hit_row);
+                            for (int c = 0; c < 32; ++c) {
+                                if (f[c] > thr) {
+                                    const int col = part * 32 + c;
+                                    if (pend_n == 0) {
+                                        pend_v0 = r[c];
+                                        pend_c0 = col;
+                                        pend_n = 1;
+                                    } else if (pend_n == 1) {
+                                        pend_v1 = r[c];
+                                        pend_c1 = col;
+                                        pend_n = 2;
+                                    } else if (row_base + col < p.n_rows) {
+                                        res = tc_append(cnt_q, cand_q, res, p.res_block, make_key(f[c], uint32_t(row_base + col)));
+                                    }
                                 }
                             }
                         }
+                        __syncwarp();
                     }
                 }
                 TRACE(3, it, blockIdx.x == 0 && warp == 5 && lane == 0);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tmem_empty[t]);
-                if (pend_n > 0) tc_append(p, res, q, __uint_as_float(pend_v0), pend_r0);
-                if (pend_n > 1) tc_append(p, res, q, __uint_as_float(pend_v1), pend_r1);
+                if (pend_n > 0 && row_base + pend_c0 < p.n_rows)
+                    res = tc_append(cnt_q, cand_q, res, p.res_block, make_key(__uint_as_float(pend_v0), uint32_t(row_base + pend_c0)));
+                if (pend_n > 1 && row_base + pend_c1 < p.n_rows)
+                    res = tc_append(cnt_q, cand_q, res, p.res_block, make_key(__uint_as_float(pend_v1), uint32_t(row_base + pend_c1)));
                 TRACE(4, it, blockIdx.x == 0 && warp == 5 && lane == 0);
             }
-            if (!p.first_round) tc_close_reservation(p, res, q);
+            if (!p.first_round) tc_close_reservation(cand_q, res, p.res_block);
             s += seg_len;
         }
     }
@@ -447,159 +525,186 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_filter_kernel(const TcG
 }
 
 // ------------------------------------------------------------------------------------------------
-// between rounds: keep each query's k' best candidates (sorted), publish the k'-th score as threshold
+// after every round: one block per query finds the rank-th largest approximate score of the query's candidates
+// (radix select on the 32-bit order-preserving score word), publishes it as the threshold and moves the candidates
+// at or above it to the front of the buffer.
+//   compact   (sample rounds): only the survivors are kept (cnt = survivors); thr[q] = the rank-th score.
+//   partition (last round):    survivors in front, every other real candidate behind them (cnt = all real
+//                              candidates, sel_cnt = survivors); thr_sel[q] = the rank-th score, thr[q] untouched.
+// Fewer than `rank` candidates: everything is kept and the threshold stays what it was.
 // ------------------------------------------------------------------------------------------------
-// Fast path of the selection: one WARP per query, candidates in registers (<= 32 per lane), the k'-th largest
-// score found by bisection on the 32-bit order-preserving score word (32 vote rounds), survivors compacted to the
-// front of the buffer.  No sort: the rounds only need the k' best as a set and the k'-th score as threshold.
-constexpr int SEL_WARP_MAX = 1024;
-__global__ void __launch_bounds__(128) tc_select_warp_kernel(uint64_t* __restrict__ cand, unsigned* __restrict__ cnt,
-                                                             float* __restrict__ thr, unsigned* __restrict__ flags, int nq,
-                                                             int kprime) {
-    const int lane = threadIdx.x & 31;
-    const int q = blockIdx.x * 4 + (threadIdx.x >> 5);
-    if (q >= nq) return;
-    const unsigned raw = cnt[q];
-    const unsigned fl = flags[q];
-    if ((fl & 4u) && raw == (fl >> 8)) return;  // nothing appended since the last truncated state
-    if (raw > unsigned(SEL_WARP_MAX)) return;    // tc_select_kernel's share
-    uint64_t* base = cand + size_t(q) * TC_CAP;
+constexpr int SEL_NT = 128;
+struct TcSelectParams {
+    uint64_t* cand;
+    unsigned* cnt;
+    float* thr;
+    float* thr_sel;
+    unsigned* sel_cnt;
+    unsigned* flags;
+    int rank;
+    int partition;
+};
+
+// Radix select in shared memory: the candidates of one query (<= 4096 keys, 32 KB) are staged once; the bits on which
+// the smallest and the largest score word differ are resolved 8 at a time (histogram with shared-memory atomics, the
+// bin that holds the rank-th largest found by one warp), so the work is proportional to the number of candidates and a
+// pass costs three barriers.  Scores of one query's candidates share their upper bits (same sign, 1-2 exponents): 3
+// passes are typical.
+__global__ void __launch_bounds__(SEL_NT) tc_select_kernel(const TcSelectParams p) {
+    __shared__ uint64_t s_key[TC_CAP];
+    __shared__ int s_hist[256];
+    __shared__ uint32_t s_part[3][SEL_NT / 32];
+    __shared__ int s_misc[4];  // [0] digit, [1] remaining rank, [2] survivors written, [3] others written
+    const int q = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    unsigned raw = p.cnt[q];
+    if (raw > unsigned(TC_CAP)) {  // candidates were lost: the query goes to the exact scan in the end
+        if (tid == 0) atomicOr(p.flags + q, 1u);
+        raw = unsigned(TC_CAP);
+    }
     const int n = int(raw);
-    uint64_t key[32];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-        const int i = j * 32 + lane;
-        key[j] = (i < n) ? base[i] : 0ull;
-    }
-    int nv = 0;  // real candidates (unused reserved slots hold key 0)
-#pragma unroll
-    for (int j = 0; j < 32; ++j) nv += (key[j] != 0ull) ? 1 : 0;
-    nv = __reduce_add_sync(FULL, nv);
-    const bool select = nv >= kprime;  // otherwise every real candidate is kept and the threshold stays
-    uint32_t T = 0;                     // k'-th largest score word
-    if (select) {
-#pragma unroll 1
-        for (int bit = 31; bit >= 0; --bit) {
-            const uint32_t c = T | (1u << bit);
-            int ge = 0;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) ge += (uint32_t(key[j] >> 32) >= c) ? 1 : 0;  // empty slots have score word 0 < c
-            if (__reduce_add_sync(FULL, ge) >= kprime) T = c;
+    uint64_t* base = p.cand + size_t(q) * TC_CAP;
+    uint32_t lmin = 0xFFFFFFFFu, lmax = 0u, real = 0u;
+    for (int i = tid; i < n; i += SEL_NT) {
+        const uint64_t key = base[i];
+        s_key[i] = key;
+        if (key != 0ull) {
+            const uint32_t h = uint32_t(key >> 32);
+            lmin = h < lmin ? h : lmin;
+            lmax = h > lmax ? h : lmax;
+            ++real;
         }
     }
-    // survivors: score word > T always; score word == T (ties at the threshold) until k' are kept
-    int above = 0;
-#pragma unroll
-    for (int j = 0; j < 32; ++j) above += (key[j] != 0ull && uint32_t(key[j] >> 32) > T) ? 1 : 0;
-    above = __reduce_add_sync(FULL, above);
-    int ties_left = select ? (kprime - above) : 0;
-    int out = 0;
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-        const uint32_t hi = uint32_t(key[j] >> 32);
-        const bool real = key[j] != 0ull;
-        const bool is_tie = select && real && hi == T;
-        const unsigned tie_mask = __ballot_sync(FULL, is_tie);
-        const bool keep = real && (!select || hi > T || (is_tie && __popc(tie_mask & ((1u << lane) - 1u)) < ties_left));
-        const unsigned keep_mask = __ballot_sync(FULL, keep);
-        if (keep) base[out + __popc(keep_mask & ((1u << lane) - 1u))] = key[j];
-        out += __popc(keep_mask);
-        const int ties_taken = __popc(tie_mask);
-        ties_left -= (ties_taken < ties_left) ? ties_taken : ties_left;
-    }
+    lmin = __reduce_min_sync(FULL, lmin);
+    lmax = __reduce_max_sync(FULL, lmax);
+    real = __reduce_add_sync(FULL, real);
     if (lane == 0) {
-        cnt[q] = unsigned(out);
-        if (select) thr[q] = unorder_f32(T);  // k'-th best approximate score over the rows seen so far
-        flags[q] = (flags[q] & 0xFFu) | 4u | (unsigned(out) << 8);
+        s_part[0][warp] = lmin;
+        s_part[1][warp] = lmax;
+        s_part[2][warp] = real;
     }
-}
-
-__global__ void __launch_bounds__(256) tc_select_kernel(uint64_t* __restrict__ cand, unsigned* __restrict__ cnt,
-                                                        float* __restrict__ thr, unsigned* __restrict__ flags,
-                                                        unsigned* __restrict__ n_flagged, int kprime) {
-    extern __shared__ uint64_t s_keys[];
-    __shared__ int s_valid;
-    const int q = blockIdx.x, tid = threadIdx.x;
-    const unsigned raw = cnt[q];
-    const unsigned fl = flags[q];
-    if ((fl & 4u) && raw == (fl >> 8)) return;  // nothing appended since the last truncated state
-    if (raw <= unsigned(SEL_WARP_MAX)) return;   // tc_select_warp_kernel's share
-    if (raw > unsigned(TC_CAP)) {  // lost candidates: the query falls back to the exact scan
-        if (tid == 0 && (atomicOr(flags + q, 1u) & 3u) == 0u) atomicAdd(n_flagged, 1u);
+    if (tid == 0) {
+        s_misc[2] = 0;
+        s_misc[3] = 0;
     }
-    const int n = int(raw < unsigned(TC_CAP) ? raw : unsigned(TC_CAP));
-    int P = 2, logP = 1;
-    while (P < n) { P <<= 1; ++logP; }
-    uint64_t* base = cand + size_t(q) * TC_CAP;
-    for (int i = tid; i < P; i += 256) s_keys[i] = (i < n) ? base[i] : 0ull;
-    if (tid == 0) s_valid = 0;
     __syncthreads();
-    // bitonic sort, descending; all strides are powers of two
-    for (int ls = 1; ls <= logP; ++ls) {
-        const int size = 1 << ls;
-        for (int lt = ls - 1; lt >= 0; --lt) {
-            const int stride = 1 << lt;
-            for (int i = tid; i < (P >> 1); i += 256) {
-                const int lo = ((i & ~(stride - 1)) << 1) | (i & (stride - 1));
-                const int hi = lo + stride;
-                const bool desc = (lo & size) == 0;
-                const uint64_t a = s_keys[lo], b = s_keys[hi];
-                if ((a < b) == desc) {
-                    s_keys[lo] = b;
-                    s_keys[hi] = a;
+    uint32_t gmin = 0xFFFFFFFFu, gmax = 0u;
+    int nv = 0;
+#pragma unroll
+    for (int w = 0; w < SEL_NT / 32; ++w) {
+        gmin = s_part[0][w] < gmin ? s_part[0][w] : gmin;
+        gmax = s_part[1][w] > gmax ? s_part[1][w] : gmax;
+        nv += int(s_part[2][w]);
+    }
+    const bool select = nv >= p.rank;
+    uint32_t T = 0;  // rank-th largest score word
+    if (select) {
+        const uint32_t diff = gmin ^ gmax;
+        if (diff == 0u) {
+            T = gmin;
+        } else {
+            int lo = 32 - __clz(diff);           // bits [0, lo) differ somewhere; the bits above are common
+            uint64_t pfx = uint64_t(gmax) >> lo;  // value of the bits resolved so far
+            int need = p.rank;
+            while (lo > 0) {  // block-uniform
+                const int w = lo < 8 ? lo : 8;
+                lo -= w;
+                for (int b = tid; b < 256; b += SEL_NT) s_hist[b] = 0;
+                __syncthreads();
+                for (int i = tid; i < n; i += SEL_NT) {
+                    const uint64_t key = s_key[i];
+                    const uint32_t h = uint32_t(key >> 32);
+                    if (key != 0ull && (uint64_t(h) >> (lo + w)) == pfx) atomicAdd(&s_hist[(h >> lo) & ((1u << w) - 1u)], 1);
                 }
+                __syncthreads();
+                if (warp == 0) {
+                    int sm = 0;
+#pragma unroll
+                    for (int b = 0; b < 8; ++b) sm += s_hist[lane * 8 + b];
+                    int S = sm;  // keys in the bins of lanes >= this one
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int v = __shfl_down_sync(FULL, S, o);
+                        if (lane + o < 32) S += v;
+                    }
+                    const int above = S - sm;
+                    if (above < need && need <= S) {  // exactly one lane
+                        int acc = above;
+                        for (int b = lane * 8 + 7; b >= lane * 8; --b) {
+                            const int hcount = s_hist[b];
+                            if (acc + hcount >= need) {
+                                s_misc[0] = b;
+                                s_misc[1] = need - acc;
+                                break;
+                            }
+                            acc += hcount;
+                        }
+                    }
+                }
+                __syncthreads();
+                pfx = (pfx << w) | uint64_t(s_misc[0]);
+                need = s_misc[1];
             }
-            __syncthreads();
+            T = uint32_t(pfx);
         }
     }
-    // unused reserved slots hold key 0 and sorted to the end: count the real candidates
-    for (int i = tid; i < P; i += 256)
-        if (s_keys[i] != 0ull && (i + 1 == P || s_keys[i + 1] == 0ull)) s_valid = i + 1;
+    // survivors (score word >= T; ties included) to the front; in partition mode the other real candidates behind them.
+    // Every key is in shared memory by now, so the buffer can be rewritten in place.
+    for (int i = tid; i < n; i += SEL_NT) {
+        const uint64_t key = s_key[i];
+        if (key != 0ull && (!select || uint32_t(key >> 32) >= T)) base[atomicAdd(&s_misc[2], 1)] = key;
+    }
     __syncthreads();
-    const int nv = s_valid;
-    const int keep = nv < kprime ? nv : kprime;
-    for (int i = tid; i < keep; i += 256) base[i] = s_keys[i];
+    const int total_k = s_misc[2];
+    if (p.partition && select) {
+        for (int i = tid; i < n; i += SEL_NT) {
+            const uint64_t key = s_key[i];
+            if (key != 0ull && uint32_t(key >> 32) < T) base[total_k + atomicAdd(&s_misc[3], 1)] = key;
+        }
+        __syncthreads();
+    }
     if (tid == 0) {
-        cnt[q] = unsigned(keep);
-        if (nv >= kprime) thr[q] = key_score(s_keys[kprime - 1]);
-        flags[q] = (flags[q] & 0xFFu) | 4u | (unsigned(keep) << 8);
+        if (p.partition) {
+            p.thr_sel[q] = select ? unorder_f32(T) : p.thr[q];
+            p.cnt[q] = unsigned(total_k + s_misc[3]);
+            p.sel_cnt[q] = unsigned(total_k);
+        } else {
+            if (select) p.thr[q] = unorder_f32(T);
+            p.cnt[q] = unsigned(total_k);
+        }
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// K4: exact fp32 rescore of the k' candidates, top-k, certificate
+// K4: exact fp32 rescore of the candidates, top-k, two-level certificate, device-side fallback queue
 // ------------------------------------------------------------------------------------------------
 struct TcRescoreParams {
     const float* rows;      // fp32 row-swizzled shard
     const float* qn;        // [nq][128] normalised queries
-    const uint64_t* cand;   // [nq][TC_CAP] sorted approximate keys
-    const unsigned* cnt;    // [nq] <= kprime
-    const float* q_norm;    // [nq] |q| as used
-    const float* thr;       // [nq] final approximate-score thresholds
+    const float* q_raw;     // [nq][128] queries as given (copied to the fallback queue)
+    const uint64_t* cand;   // [nq][TC_CAP] approximate keys: [0, sel_cnt) the k' best, [sel_cnt, cnt) the rest
+    const unsigned* cnt;
+    const unsigned* sel_cnt;
+    const float* eps;       // [nq] certificate slack
+    const float* thr;       // [nq] threshold of the last GEMM round
+    const float* thr_sel;   // [nq] k'-th best approximate score (== thr when fewer than k' candidates)
     unsigned* flags;
-    unsigned* n_flagged;
-    int nq, k, kprime;
+    unsigned* n_flagged;    // length of the fallback queue
+    int* fb_list;           // [nq] queued query indices
+    float* fb_q;            // [nq][128] their raw queries
+    int nq, k;
     uint32_t id_base;
-    float eps_rel;          // 0.004 * max |row|
     uint64_t* out_keys;
     float* out_scores;
     int64_t* out_ids;
 };
 
-__global__ void __launch_bounds__(128) tc_rescore_kernel(const TcRescoreParams p) {
-    const int lane = threadIdx.x & 31;
-    const int q = blockIdx.x * 4 + (threadIdx.x >> 5);
-    if (q >= p.nq) return;
-    const int n = int(p.cnt[q]);
-    const uint64_t* cand = p.cand + size_t(q) * TC_CAP;
-    const float4* q4 = reinterpret_cast<const float4*>(p.qn + size_t(q) * DIM);
-    WarpTopK<4> tk;
-    tk.init();
+// offer candidates [c_begin, c_end) of the query, rescored exactly, to the warp's top-k list
+__device__ __forceinline__ void rescore_range(const TcRescoreParams& p, const uint64_t* cand, const float4* q4, int c_begin, int c_end,
+                                              WarpTopK<4>& tk, int lane) {
     constexpr int U = 8;  // candidate rows in flight per warp
-    uint64_t batch = 0;   // lane i holds the exact key of candidate (c0 + i) of the current 32-batch
-    for (int c0 = 0; c0 < n; c0 += 32) {
-        batch = 0;
-        for (int u0 = 0; u0 < 32 && c0 + u0 < n; u0 += U) {
+    for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+        uint64_t batch = 0;  // lane i holds the exact key of candidate (c0 + i)
+        for (int u0 = 0; u0 < 32 && c0 + u0 < c_end; u0 += U) {
             float part[U];
             int64_t rowid[U];
 #pragma unroll
@@ -607,12 +712,14 @@ __global__ void __launch_bounds__(128) tc_rescore_kernel(const TcRescoreParams p
                 const int c = c0 + u0 + u;
                 part[u] = 0.f;
                 rowid[u] = -1;
-                if (c < n) {
+                if (c < c_end) {
                     const int64_t row = key_id(cand[c]);
                     rowid[u] = row;
-                    const float4 v = reinterpret_cast<const float4*>(p.rows + row * DIM)[lane];  // physical chunk `lane`
-                    const float4 w = q4[swz_chunk(lane, row)];                                    // = logical chunk
-                    part[u] = fmaf(v.w, w.w, fmaf(v.z, w.z, fmaf(v.y, w.y, v.x * w.x)));
+                    if (row >= 0) {
+                        const float4 v = reinterpret_cast<const float4*>(p.rows + row * DIM)[lane];  // physical chunk `lane`
+                        const float4 w = q4[swz_chunk(lane, row)];                                    // = logical chunk
+                        part[u] = fmaf(v.w, w.w, fmaf(v.z, w.z, fmaf(v.y, w.y, v.x * w.x)));
+                    }
                 }
             }
 #pragma unroll
@@ -625,17 +732,44 @@ __global__ void __launch_bounds__(128) tc_rescore_kernel(const TcRescoreParams p
         }
         tk.offer(batch, lane, p.k);
     }
-    // certificate: every row that is NOT a candidate has approximate score <= t' (the k'-th approximate
-    // score) and therefore exact score <= t' + eps; the result is exact if the k-th exact score beats that.
-    bool ok = true;
-    if (n >= p.kprime) {
-        const float tprime = p.thr[q];  // k'-th best approximate score over all rows (last selection)
-        const float sk = key_score(tk.thr);  // k-th best exact (thr == 0 -> -inf if fewer than k candidates)
-        const float eps = p.eps_rel * p.q_norm[q] + 2e-5f;
-        ok = sk > tprime + eps;
+}
+
+__global__ void __launch_bounds__(128) tc_rescore_kernel(const TcRescoreParams p) {
+    const int lane = threadIdx.x & 31;
+    const int q = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (q >= p.nq) return;
+    const int n_all = int(p.cnt[q]);
+    const int n_sel = int(p.sel_cnt[q]);
+    const unsigned fl = p.flags[q];
+    const uint64_t* cand = p.cand + size_t(q) * TC_CAP;
+    const float4* q4 = reinterpret_cast<const float4*>(p.qn + size_t(q) * DIM);
+    const float eps = p.eps[q];
+    WarpTopK<4> tk;
+    tk.init();
+    // Phase A.  Every row that is NOT among the k' selected candidates has an approximate score <= t' and therefore an
+    // exact score <= t' + eps: the k best of the candidates are the k best of the shard if the k-th exact score beats that.
+    // t' = -inf means every row of the shard is a candidate (shards of at most 4096 rows with fewer than k' rows).
+    rescore_range(p, cand, q4, 0, n_sel, tk, lane);
+    bool ok = false;
+    if (!(fl & 1u)) {
+        const float tprime = p.thr_sel[q];
+        ok = (tprime == -INFINITY) || (key_score(tk.thr) > tprime + eps);
+        if (!ok && n_all > n_sel) {
+            // Phase B: all the rows above the last round's threshold are in the buffer; rescore the rest of them too.
+            rescore_range(p, cand, q4, n_sel, n_all, tk, lane);
+            const float tround = p.thr[q];
+            ok = (tround == -INFINITY) || (key_score(tk.thr) > tround + eps);
+        }
     }
-    if (!ok && lane == 0) {
-        if ((atomicOr(p.flags + q, 2u) & 3u) == 0u) atomicAdd(p.n_flagged, 1u);
+    if (!ok) {  // queue the query for the exact scan (device-side: the scan kernels read the queue length themselves)
+        unsigned slot = 0;
+        if (lane == 0) {
+            slot = atomicAdd(p.n_flagged, 1u);
+            p.fb_list[slot] = q;
+            p.flags[q] = fl | 2u;
+        }
+        slot = __shfl_sync(FULL, slot, 0);
+        reinterpret_cast<float4*>(p.fb_q + size_t(slot) * DIM)[lane] = reinterpret_cast<const float4*>(p.q_raw + size_t(q) * DIM)[lane];
     }
     const size_t base = size_t(q) * p.k;
 #pragma unroll
@@ -662,7 +796,25 @@ int tc_fail(int code, const char* what, cudaError_t e) {
         if (e__ != cudaSuccess) return tc_fail(e__ == cudaErrorMemoryAllocation ? FCS_ERR_NOMEM : FCS_ERR_CUDA, #call, e__); \
     } while (0)
 
+double env_double(const char* name, double dflt, double lo, double hi) {
+    if (const char* s = getenv(name)) {
+        const double v = atof(s);
+        if (v >= lo && v <= hi) return v;
+    }
+    return dflt;
+}
+
 }  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// round plan (host)
+// ------------------------------------------------------------------------------------------------
+struct TcRound {
+    int64_t n_idx, j0, stride, comp_T;
+    int first;
+    int rank;       // selection rank after the round
+    int partition;  // last round: partition instead of compact
+};
 
 struct TcState {
     int device = 0, sm_count = 0;
@@ -670,41 +822,136 @@ struct TcState {
     int64_t n_rows = 0, n_tiles = 0;
     uint32_t id_base = 0;
     uint8_t* b_img = nullptr;
-    float max_norm = 1.f;
+    float max_rhat = 1.f, max_dr = 0.f;
     // per-search workspace, grown on demand
     int nq_cap = 0;
     float* qn = nullptr;
     uint8_t* a_img = nullptr;
     float* thr = nullptr;
+    float* thr_sel = nullptr;
     unsigned* cnt = nullptr;
+    unsigned* sel_cnt = nullptr;
     uint64_t* cand = nullptr;
     unsigned* flags = nullptr;
-    float* q_norm = nullptr;
-    unsigned* n_flagged = nullptr;
-    unsigned* h_n_flagged = nullptr;  // pinned
-    unsigned* h_flags = nullptr;      // pinned, nq_cap
-    double growth = 2.0;  // rows seen grow x3 per round; measured best on B200 (profiles/r01_ncu_summary.md)
+    float* eps = nullptr;
+    int* fb_list = nullptr;
+    float* fb_q = nullptr;
+    unsigned* n_flagged = nullptr;    // device: [0] fallback queue length, [1..2] build statistics
+    unsigned* h_n_flagged = nullptr;  // pinned copy of [0], refreshed at the end of every search
+    // plan parameters (FCS_TC_* environment overrides, for sweeps)
+    double cf_mult = 3.0, cf_min = 512.0, m_final = 24.0, c_sample = 128.0, m_min = 16.0;
     bool verbose = false;
     // timing of the dominant kernel: one event pair per K3 launch of the last search
-    static constexpr int MAX_ROUNDS = 48;
+    static constexpr int MAX_ROUNDS = 16;
     cudaEvent_t ev[2 * MAX_ROUNDS] = {};
-    float last_k3_ms = 0.f;
+    cudaEvent_t ev_done = nullptr;
     int last_rounds = 0;
+    bool last_valid = false;
+    // FCS_TC_PHASES=1: an event in front of every kernel of a search, printed by tc_last_kernel_ms (diagnostics)
+    bool phases = false;
+    int r0_tiles = TC_R0_TILES;
+    std::vector<cudaEvent_t> pev;
+    std::vector<std::string> plabel;
+    int n_pev = 0;
 };
+
+static void tc_phase(TcState* s, const char* label, cudaStream_t stream) {
+    if (!s->phases) return;
+    if (s->n_pev >= int(s->pev.size())) {
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) return;
+        s->pev.push_back(e);
+        s->plabel.emplace_back();
+    }
+    s->plabel[s->n_pev] = label;
+    cudaEventRecord(s->pev[s->n_pev++], stream);
+}
+
+static std::vector<TcRound> tc_plan(const TcState* s, int kp) {
+    std::vector<TcRound> plan;
+    const int64_t nt = s->n_tiles;
+    if (nt <= TC_R0_TILES) {  // the whole shard fits the candidate buffer: one round records everything
+        plan.push_back({nt, 0, 1, 0, 1, kp, 1});
+        return plan;
+    }
+    const int64_t t0 = nt / 2 < s->r0_tiles ? nt / 2 : s->r0_tiles;
+    const double cf = std::fmax(s->cf_mult * kp, s->cf_min);  // rows expected above the sweep threshold
+    int64_t t_last = int64_t(std::ceil(double(nt) * s->m_final / cf));
+    if (t_last > nt / 2) t_last = nt / 2;
+    if (t_last < t0) t_last = t0;
+    const int64_t stride = nt / t_last;  // >= 2
+    auto clamp_rank = [](double r) { return int(r < 1.0 ? 1.0 : (r > double(TC_MAX_RANK) ? double(TC_MAX_RANK) : std::ceil(r))); };
+    // nested samples t0 < T_1 < ... < t_last, each at most c_sample/m_min times the previous
+    std::vector<int64_t> ts{t0};
+    if (t_last > t0) {
+        const double ratio = double(t_last) / double(t0);
+        int ns = int(std::ceil(std::log(ratio) / std::log(s->c_sample / s->m_min) - 1e-9));
+        if (ns < 1) ns = 1;
+        for (int i = 1; i <= ns; ++i) {
+            int64_t t = (i == ns) ? t_last : int64_t(std::llround(double(t0) * std::pow(ratio, double(i) / ns)));
+            if (t <= ts.back()) t = ts.back() + 1;
+            if (t > t_last) t = t_last;
+            if (t > ts.back()) ts.push_back(t);
+        }
+    }
+    for (size_t i = 0; i < ts.size(); ++i) {
+        TcRound r = {};
+        r.j0 = i == 0 ? 0 : ts[i - 1];
+        r.n_idx = ts[i] - r.j0;
+        r.stride = stride;
+        r.first = i == 0 ? 1 : 0;
+        const double seen = double(ts[i]);
+        const double next = (i + 1 < ts.size()) ? double(ts[i + 1] - ts[i]) : double(nt - ts[i]);
+        const double target = (i + 1 < ts.size()) ? s->c_sample : cf;
+        r.rank = clamp_rank(target * seen / next);
+        plan.push_back(r);
+    }
+    TcRound sweep = {};
+    sweep.n_idx = nt - t_last;
+    sweep.stride = stride;
+    sweep.comp_T = t_last;
+    sweep.rank = kp;
+    sweep.partition = 1;
+    plan.push_back(sweep);
+    return plan;
+}
 
 const char* tc_last_error() { return g_tc_error.c_str(); }
 int tc_min_batch() { return 32; }
 int tc_max_k() { return 128; }
-float tc_last_kernel_ms(const TcState* s) { return s ? s->last_k3_ms : 0.f; }
 int tc_last_rounds(const TcState* s) { return s ? s->last_rounds : 0; }
 uint64_t tc_image_bytes(const TcState* s) { return s ? uint64_t(s->n_tiles) * B_TILE_BYTES : 0; }
 
+float tc_last_kernel_ms(TcState* s) {
+    if (!s || !s->last_valid) return 0.f;
+    if (cudaEventSynchronize(s->ev_done) != cudaSuccess) return 0.f;
+    float total = 0.f;
+    if (s->phases) {
+        for (int i = 0; i + 1 < s->n_pev; ++i) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, s->pev[i], s->pev[i + 1]);
+            fprintf(stderr, "[fcs_tc] phase %-10s %8.1f us\n", s->plabel[i].c_str(), ms * 1e3f);
+        }
+    }
+    for (int r = 0; r < s->last_rounds && r < TcState::MAX_ROUNDS; ++r) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, s->ev[2 * r], s->ev[2 * r + 1]) == cudaSuccess) total += ms;
+        if (s->verbose) fprintf(stderr, "[fcs_tc] round %d: gemm+filter %.3f ms\n", r, ms);
+    }
+    return total;
+}
+
+int tc_last_flagged(TcState* s) {
+    if (!s || !s->last_valid) return 0;
+    if (cudaEventSynchronize(s->ev_done) != cudaSuccess) return 0;
+    return int(s->h_n_flagged[0]);
+}
+
 static void tc_free_workspace(TcState* s) {
-    cudaFree(s->qn); cudaFree(s->a_img); cudaFree(s->thr); cudaFree(s->cnt); cudaFree(s->cand);
-    cudaFree(s->flags); cudaFree(s->q_norm);
-    if (s->h_flags) cudaFreeHost(s->h_flags);
-    s->qn = nullptr; s->a_img = nullptr; s->thr = nullptr; s->cnt = nullptr; s->cand = nullptr;
-    s->flags = nullptr; s->q_norm = nullptr; s->h_flags = nullptr;
+    cudaFree(s->qn); cudaFree(s->a_img); cudaFree(s->thr); cudaFree(s->thr_sel); cudaFree(s->cnt); cudaFree(s->sel_cnt);
+    cudaFree(s->cand); cudaFree(s->flags); cudaFree(s->eps); cudaFree(s->fb_list); cudaFree(s->fb_q);
+    s->qn = nullptr; s->a_img = nullptr; s->thr = nullptr; s->thr_sel = nullptr; s->cnt = nullptr; s->sel_cnt = nullptr;
+    s->cand = nullptr; s->flags = nullptr; s->eps = nullptr; s->fb_list = nullptr; s->fb_q = nullptr;
     s->nq_cap = 0;
 }
 
@@ -713,6 +960,8 @@ void tc_destroy(TcState* s) {
     tc_free_workspace(s);
     for (cudaEvent_t e : s->ev)
         if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : s->pev) cudaEventDestroy(e);
+    if (s->ev_done) cudaEventDestroy(s->ev_done);
     cudaFree(s->b_img);
     cudaFree(s->n_flagged);
     if (s->h_n_flagged) cudaFreeHost(s->h_n_flagged);
@@ -730,34 +979,39 @@ int tc_create(TcState** out, int device, int sm_count, const float* rows, int64_
     s->id_base = id_base;
     s->n_tiles = (n_rows + TC_N - 1) / TC_N;
     s->verbose = getenv("FCS_TC_VERBOSE") != nullptr;
-    if (const char* g = getenv("FCS_TC_GROWTH")) {
-        const double v = atof(g);
-        if (v >= 1.25 && v <= 16.0) s->growth = v;
-    }
+    s->cf_mult = env_double("FCS_TC_CF_MULT", s->cf_mult, 1.0, 16.0);
+    s->cf_min = env_double("FCS_TC_CF_MIN", s->cf_min, 32.0, 2048.0);
+    s->m_final = env_double("FCS_TC_M_FINAL", s->m_final, 2.0, 256.0);
+    s->c_sample = env_double("FCS_TC_C_SAMPLE", s->c_sample, 64.0, 2048.0);
+    s->m_min = env_double("FCS_TC_M_MIN", s->m_min, 1.0, 64.0);
+    s->r0_tiles = int(env_double("FCS_TC_R0_TILES", TC_R0_TILES, 1.0, TC_R0_TILES));
+    s->phases = getenv("FCS_TC_PHASES") != nullptr;
     auto run = [&]() -> int {
         TC_CUDA(cudaFuncSetAttribute(tc_gemm_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
-        TC_CUDA(cudaFuncSetAttribute(tc_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_CAP * 8));
         // the small kernels between two GEMM launches ask for the same shared-memory carve-out as the GEMM kernel,
         // so the SMs are not reconfigured (drained) twice per round
-        TC_CUDA(cudaFuncSetAttribute(tc_select_warp_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         TC_CUDA(cudaFuncSetAttribute(tc_select_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         TC_CUDA(cudaFuncSetAttribute(tc_prep_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         TC_CUDA(cudaFuncSetAttribute(tc_rescore_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         for (cudaEvent_t& e : s->ev) TC_CUDA(cudaEventCreate(&e));
+        TC_CUDA(cudaEventCreateWithFlags(&s->ev_done, cudaEventDisableTiming));
         TC_CUDA(cudaMalloc(&s->b_img, size_t(s->n_tiles) * B_TILE_BYTES));
-        TC_CUDA(cudaMalloc(&s->n_flagged, 2 * sizeof(unsigned)));
-        TC_CUDA(cudaMallocHost(&s->h_n_flagged, 2 * sizeof(unsigned)));
-        TC_CUDA(cudaMemsetAsync(s->n_flagged, 0, 2 * sizeof(unsigned), stream));
+        TC_CUDA(cudaMalloc(&s->n_flagged, 4 * sizeof(unsigned)));
+        TC_CUDA(cudaMallocHost(&s->h_n_flagged, 4 * sizeof(unsigned)));
+        TC_CUDA(cudaMemsetAsync(s->n_flagged, 0, 4 * sizeof(unsigned), stream));
         const int64_t total = s->n_tiles * TC_N * 16;
         int64_t g = (total + 255) / 256;
         if (g > sm_count * 16) g = sm_count * 16;
         tc_build_bimg_kernel<<<int(g), 256, 0, stream>>>(rows, n_rows, s->n_tiles, s->b_img, s->n_flagged + 1);
         TC_CUDA(cudaGetLastError());
-        TC_CUDA(cudaMemcpyAsync(s->h_n_flagged, s->n_flagged, 2 * sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
+        TC_CUDA(cudaMemcpyAsync(s->h_n_flagged, s->n_flagged, 4 * sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
         TC_CUDA(cudaStreamSynchronize(stream));
-        float n2;
+        float n2, d2;
         memcpy(&n2, &s->h_n_flagged[1], 4);
-        s->max_norm = sqrtf(n2);
+        memcpy(&d2, &s->h_n_flagged[2], 4);
+        s->max_rhat = sqrtf(n2) * 1.0001f;
+        s->max_dr = sqrtf(d2) * 1.0001f;
+        s->h_n_flagged[0] = 0;
         return FCS_OK;
     };
     const int rc = run();
@@ -776,26 +1030,54 @@ static int tc_ensure_workspace(TcState* s, int nq) {
     TC_CUDA(cudaMalloc(&s->qn, size_t(nq_pad) * DIM * 4));
     TC_CUDA(cudaMalloc(&s->a_img, size_t(nq_pad / TC_M) * A_TILE_BYTES));
     TC_CUDA(cudaMalloc(&s->thr, size_t(nq_pad) * 4));
+    TC_CUDA(cudaMalloc(&s->thr_sel, size_t(nq_pad) * 4));
     TC_CUDA(cudaMalloc(&s->cnt, size_t(nq_pad) * 4));
+    TC_CUDA(cudaMalloc(&s->sel_cnt, size_t(nq_pad) * 4));
     TC_CUDA(cudaMalloc(&s->flags, size_t(nq_pad) * 4));
-    TC_CUDA(cudaMalloc(&s->q_norm, size_t(nq_pad) * 4));
+    TC_CUDA(cudaMalloc(&s->eps, size_t(nq_pad) * 4));
+    TC_CUDA(cudaMalloc(&s->fb_list, size_t(nq_pad) * 4));
+    TC_CUDA(cudaMalloc(&s->fb_q, size_t(nq_pad) * DIM * 4));
     TC_CUDA(cudaMalloc(&s->cand, size_t(nq_pad) * TC_CAP * 8));
-    TC_CUDA(cudaMallocHost(&s->h_flags, size_t(nq_pad) * 4));
     s->nq_cap = nq_pad;
     return FCS_OK;
 }
 
 int tc_default_kprime(int k) {
-    // margin for the exactness certificate: the bf16 rounding bound eps covers a few dozen ranks at TED scale
+    // margin for the exactness certificate: eps (~0.0035 for unit vectors) covers a few dozen ranks at TED scale
     int kp = k + (k * 6 / 10 > 32 ? k * 6 / 10 : 32);
     kp = (kp + 31) / 32 * 32;
     return kp > TC_MAX_KPRIME ? TC_MAX_KPRIME : kp;
 }
 
+static void tc_launch_prep(TcState* s, const float* q_dev, int nq, int nq_pad, int qnorm, unsigned first_slots, cudaStream_t stream) {
+    TcPrepParams pp = {};
+    pp.q_raw = q_dev; pp.nq = nq; pp.nq_pad = nq_pad; pp.qnorm = qnorm;
+    pp.qn = s->qn; pp.a_img = s->a_img; pp.thr = s->thr; pp.thr_sel = s->thr_sel; pp.cnt = s->cnt; pp.sel_cnt = s->sel_cnt;
+    pp.flags = s->flags; pp.eps = s->eps; pp.n_flagged = s->n_flagged; pp.first_round_slots = first_slots;
+    pp.max_rhat = s->max_rhat; pp.max_dr = s->max_dr;
+    tc_prep_kernel<<<(nq_pad + 3) / 4, 128, 0, stream>>>(pp);
+}
+
+static void tc_launch_gemm(TcState* s, const TcRound& r, int nq, int n_qgroups, cudaStream_t stream, int trace_on) {
+    TcGemmParams gp = {};
+    gp.a_img = s->a_img; gp.b_img = s->b_img; gp.n_rows = s->n_rows; gp.nq = nq; gp.n_qgroups = n_qgroups;
+    gp.n_idx = r.n_idx; gp.j0 = r.j0; gp.stride = r.stride; gp.comp_T = r.comp_T;
+    gp.thr = s->thr; gp.cnt = s->cnt; gp.cand = s->cand; gp.first_round = r.first; gp.trace_on = trace_on;
+    const int64_t steps = int64_t(n_qgroups) * r.n_idx;
+    const int grid = int(steps < s->sm_count ? steps : s->sm_count);
+    // every thread that appends at all rounds its reservation up to res_block slots: keep the waste of the
+    // ~grid/n_qgroups segments that share a query below ~512 slots
+    const int segs = (grid + n_qgroups - 1) / n_qgroups + 1;
+    const int rb = 512 / segs;
+    gp.res_block = rb < 2 ? 2 : (rb > TC_RES_MAX ? TC_RES_MAX : rb);
+    tc_gemm_filter_kernel<<<grid, TC_THREADS, TC_SMEM, stream>>>(gp);
+}
+
+// Enqueues the whole batched search on `stream` and returns without synchronising.  Queries whose certificate failed
+// are queued on the device (fallback queue: *fb_count_dev entries of fb_list_dev / fb_q_dev); the caller launches the
+// exact scan over that queue.
 int tc_search(TcState* s, const float* q_dev, int nq, int k, int kprime, int qnorm, float* out_scores, int64_t* out_ids,
-              uint64_t* out_keys, cudaStream_t stream, int* launches, const unsigned** flagged_host, int* n_flagged_out) {
-    *n_flagged_out = 0;
-    *flagged_host = nullptr;
+              uint64_t* out_keys, cudaStream_t stream, int* launches, TcFallbackQueue* fbq) {
     if (k > tc_max_k()) {
         g_tc_error = "k too large for the tensor-core path";
         return FCS_ERR_UNSUPPORTED;
@@ -807,113 +1089,99 @@ int tc_search(TcState* s, const float* q_dev, int nq, int k, int kprime, int qno
     if (rc != FCS_OK) return rc;
     const int n_qgroups = (nq + TC_QGROUP - 1) / TC_QGROUP;
     const int nq_pad = n_qgroups * TC_QGROUP;
+    const std::vector<TcRound> plan = tc_plan(s, kp);
 
-    // the first round (threshold -inf: every row is a candidate) covers at most CAP/2 rows and indexes by row
-    const int64_t first_tiles = SEL_WARP_MAX / TC_N;
-    const int64_t first_rows = (first_tiles * TC_N < s->n_rows) ? first_tiles * TC_N : s->n_rows;
-    tc_prep_kernel<<<(nq_pad + 3) / 4, 128, 0, stream>>>(q_dev, nq, nq_pad, qnorm, s->qn, s->a_img, s->thr, s->cnt, s->flags,
-                                                         s->q_norm, s->n_flagged, unsigned(first_rows));
+    s->n_pev = 0;
+    tc_phase(s, "prep", stream);
+    tc_launch_prep(s, q_dev, nq, nq_pad, qnorm, unsigned(plan[0].n_idx * TC_N), stream);
     TC_CUDA(cudaGetLastError());
     ++*launches;
 
-    TcGemmParams gp = {};
-    gp.a_img = s->a_img;
-    gp.b_img = s->b_img;
-    gp.n_rows = s->n_rows;
-    gp.nq = nq;
-    gp.n_qgroups = n_qgroups;
-    gp.thr = s->thr;
-    gp.cnt = s->cnt;
-    gp.cand = s->cand;
-    // rounds: a round over R rows appends about k' * R / seen keys per query
-    int64_t seen = 0;
+    static const int trace_round = getenv("FCS_TC_TRACE_ROUND") ? atoi(getenv("FCS_TC_TRACE_ROUND")) : -1;
     int rounds = 0;
-    int64_t round_tiles = first_tiles;
-    while (seen < s->n_tiles) {
-        const int64_t t1 = (seen + round_tiles < s->n_tiles) ? (seen + round_tiles) : s->n_tiles;
-        gp.tile0 = seen;
-        gp.tile1 = t1;
-        gp.first_round = rounds == 0 ? 1 : 0;
-        gp.trace_on = (getenv("FCS_TC_TRACE_ROUND") ? atoi(getenv("FCS_TC_TRACE_ROUND")) : 7) == rounds;
-        const int64_t steps = int64_t(n_qgroups) * (t1 - seen);
-        const int grid = int(steps < s->sm_count ? steps : s->sm_count);
-        {   // every thread that appends at all rounds its reservation up to res_block slots: keep the waste of the
-            // ~grid/n_qgroups segments that share a query below ~512 slots so the buffers stay in the warp-select range
-            const int segs = (grid + n_qgroups - 1) / n_qgroups + 1;
-            int rb = 512 / segs;
-            gp.res_block = rb < 2 ? 2 : (rb > TC_RES_MAX ? TC_RES_MAX : rb);
-        }
+    for (const TcRound& r : plan) {
         const bool timed = rounds < TcState::MAX_ROUNDS;
+        tc_phase(s, r.first ? "gemm-dump" : (r.comp_T ? "gemm-sweep" : "gemm-sample"), stream);
         if (timed) TC_CUDA(cudaEventRecord(s->ev[2 * rounds], stream));
-        tc_gemm_filter_kernel<<<grid, TC_THREADS, TC_SMEM, stream>>>(gp);
+        tc_launch_gemm(s, r, nq, n_qgroups, stream, trace_round == rounds ? 1 : 0);
         TC_CUDA(cudaGetLastError());
         if (timed) TC_CUDA(cudaEventRecord(s->ev[2 * rounds + 1], stream));
+        tc_phase(s, "select", stream);
+        TcSelectParams sp = {s->cand, s->cnt, s->thr, s->thr_sel, s->sel_cnt, s->flags, r.rank, r.partition};
+        tc_select_kernel<<<nq, SEL_NT, 0, stream>>>(sp);
+        TC_CUDA(cudaGetLastError());
+        *launches += 2;
+        if (s->verbose)
+            fprintf(stderr, "[fcs_tc] round %d: %s tiles=%lld j0=%lld stride=%lld comp_T=%lld rank=%d%s\n", rounds,
+                    r.first ? "dump" : (r.comp_T ? "sweep" : "sample"), (long long)r.n_idx, (long long)r.j0, (long long)r.stride,
+                    (long long)r.comp_T, r.rank, r.partition ? " (partition)" : "");
         ++rounds;
-        tc_select_warp_kernel<<<(nq + 3) / 4, 128, 0, stream>>>(s->cand, s->cnt, s->thr, s->flags, nq, kp);
-        TC_CUDA(cudaGetLastError());
-        tc_select_kernel<<<nq, 256, TC_CAP * 8, stream>>>(s->cand, s->cnt, s->thr, s->flags, s->n_flagged, kp);
-        TC_CUDA(cudaGetLastError());
-        *launches += 3;
-        seen = t1;
-        double g = double(TC_CAP - kp) / (2.0 * kp);
-        if (g > s->growth) g = s->growth;
-        if (g < 0.25) g = 0.25;
-        round_tiles = int64_t(double(seen) * g);
-        if (round_tiles < 1) round_tiles = 1;
     }
 
     TcRescoreParams rp = {};
-    rp.rows = s->rows;
-    rp.qn = s->qn;
-    rp.cand = s->cand;
-    rp.cnt = s->cnt;
-    rp.q_norm = s->q_norm;
-    rp.thr = s->thr;
-    rp.flags = s->flags;
-    rp.n_flagged = s->n_flagged;
-    rp.nq = nq;
-    rp.k = k;
-    rp.kprime = kp;
-    rp.id_base = s->id_base;
-    rp.eps_rel = 0.004f * s->max_norm;
-    rp.out_keys = out_keys;
-    rp.out_scores = out_scores;
-    rp.out_ids = out_ids;
+    rp.rows = s->rows; rp.qn = s->qn; rp.q_raw = q_dev; rp.cand = s->cand; rp.cnt = s->cnt; rp.sel_cnt = s->sel_cnt;
+    rp.eps = s->eps; rp.thr = s->thr; rp.thr_sel = s->thr_sel; rp.flags = s->flags; rp.n_flagged = s->n_flagged;
+    rp.fb_list = s->fb_list; rp.fb_q = s->fb_q; rp.nq = nq; rp.k = k; rp.id_base = s->id_base;
+    rp.out_keys = out_keys; rp.out_scores = out_scores; rp.out_ids = out_ids;
+    tc_phase(s, "rescore", stream);
     tc_rescore_kernel<<<(nq + 3) / 4, 128, 0, stream>>>(rp);
     TC_CUDA(cudaGetLastError());
     ++*launches;
-
-    // which queries need the exact fallback?  (host decision: one small synchronous read-back)
+    tc_phase(s, "tail", stream);
     TC_CUDA(cudaMemcpyAsync(s->h_n_flagged, s->n_flagged, sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
-    TC_CUDA(cudaStreamSynchronize(stream));
+    tc_phase(s, "end", stream);
+    TC_CUDA(cudaEventRecord(s->ev_done, stream));
+    s->last_rounds = rounds;
+    s->last_valid = true;
+    fbq->count_dev = s->n_flagged;
+    fbq->list_dev = s->fb_list;
+    fbq->q_dev = s->fb_q;
+    fbq->count_host = s->h_n_flagged;
 #ifdef FCS_TC_TRACE
     {
+        TC_CUDA(cudaStreamSynchronize(stream));
         static long long h[5][256];
         cudaMemcpyFromSymbol(h, g_trace, sizeof h);
-        fprintf(stderr, "[fcs_tc trace, last round, CTA 0, cycles relative to first stamp]\n it  mma_ready mma_issued | epi_full epi_done epi_arrived\n");
+        fprintf(stderr, "[fcs_tc trace, CTA 0, cycles relative to first stamp]\n it  mma_ready mma_issued | epi_full epi_done epi_arrived\n");
         for (int i = 100; i < 116; ++i)
             fprintf(stderr, "%3d  %9lld %9lld | %9lld %9lld %9lld\n", i, h[0][i] - h[0][100], h[1][i] - h[0][100], h[2][i] - h[0][100],
                     h[3][i] - h[0][100], h[4][i] - h[0][100]);
     }
 #endif
-    s->last_k3_ms = 0.f;
-    s->last_rounds = rounds;
-    for (int r = 0; r < rounds && r < TcState::MAX_ROUNDS; ++r) {
-        float ms = 0.f;
-        if (cudaEventElapsedTime(&ms, s->ev[2 * r], s->ev[2 * r + 1]) == cudaSuccess) s->last_k3_ms += ms;
-        if (s->verbose) fprintf(stderr, "[fcs_tc] round %d: gemm+filter %.3f ms\n", r, ms);
-    }
-    if (s->h_n_flagged[0] > 0) {
-        TC_CUDA(cudaMemcpyAsync(s->h_flags, s->flags, size_t(nq) * 4, cudaMemcpyDeviceToHost, stream));
-        TC_CUDA(cudaStreamSynchronize(stream));
-        *n_flagged_out = int(s->h_n_flagged[0]);
-        *flagged_host = s->h_flags;
-    }
     return FCS_OK;
 }
 
+// Test hook: the round plan for a shard of n_rows rows and a given k' (what tc_search would launch).
+int tc_debug_plan(int64_t n_rows, int kprime, int64_t* out, int max_rounds) {
+    TcState s;
+    s.n_rows = n_rows;
+    s.n_tiles = (n_rows + TC_N - 1) / TC_N;
+    const std::vector<TcRound> plan = tc_plan(&s, kprime);
+    int n = 0;
+    for (const TcRound& r : plan) {
+        if (n >= max_rounds) break;
+        int64_t* o = out + size_t(n) * 7;
+        o[0] = r.n_idx; o[1] = r.j0; o[2] = r.stride; o[3] = r.comp_T; o[4] = r.first; o[5] = r.rank; o[6] = r.partition;
+        ++n;
+    }
+    return n;
+}
+
+// Test hook: the DB tile a round visits at position idx (host mirror of tile_of, for the plan tests).
+int64_t tc_debug_tile_of(int64_t j0, int64_t stride, int64_t comp_T, int64_t idx) {
+    TcGemmParams p = {};
+    p.j0 = j0; p.stride = stride; p.comp_T = comp_T;
+    if (p.comp_T == 0) return (p.j0 + idx) * p.stride;
+    const int64_t gap = p.stride - 1, body = p.comp_T * gap;
+    if (idx < body) {
+        const int64_t b = idx / gap;
+        return b * p.stride + 1 + (idx - b * gap);
+    }
+    return idx + p.comp_T;
+}
+
 // Test hook: approximate (bf16 tensor-core) scores of every (query, row) pair, for shards of at most
-// TC_CAP rows.  One K3 launch over all tiles with the threshold at -inf appends every row.
+// TC_CAP rows.  One K3 launch in round-0 mode over all tiles records every score.
 int tc_debug_approx(TcState* s, const float* q_dev, int nq, int qnorm, float* out_host, cudaStream_t stream) {
     if (s->n_rows > TC_CAP) {
         g_tc_error = "tc_debug_approx: shard larger than the candidate buffer";
@@ -923,28 +1191,18 @@ int tc_debug_approx(TcState* s, const float* q_dev, int nq, int qnorm, float* ou
     if (rc != FCS_OK) return rc;
     const int n_qgroups = (nq + TC_QGROUP - 1) / TC_QGROUP;
     const int nq_pad = n_qgroups * TC_QGROUP;
-    tc_prep_kernel<<<(nq_pad + 3) / 4, 128, 0, stream>>>(q_dev, nq, nq_pad, qnorm, s->qn, s->a_img, s->thr, s->cnt, s->flags,
-                                                         s->q_norm, s->n_flagged, unsigned(s->n_rows));
+    tc_launch_prep(s, q_dev, nq, nq_pad, qnorm, unsigned(s->n_tiles * TC_N), stream);
     TC_CUDA(cudaGetLastError());
-    TcGemmParams gp = {};
-    gp.first_round = 1;
-    gp.res_block = TC_RES_MAX;
-    gp.a_img = s->a_img; gp.b_img = s->b_img; gp.n_rows = s->n_rows; gp.nq = nq; gp.n_qgroups = n_qgroups;
-    gp.thr = s->thr; gp.cnt = s->cnt; gp.cand = s->cand; gp.tile0 = 0; gp.tile1 = s->n_tiles;
-    const int64_t steps = int64_t(n_qgroups) * s->n_tiles;
-    tc_gemm_filter_kernel<<<int(steps < s->sm_count ? steps : s->sm_count), TC_THREADS, TC_SMEM, stream>>>(gp);
+    const TcRound r0 = {s->n_tiles, 0, 1, 0, 1, 1, 0};
+    tc_launch_gemm(s, r0, nq, n_qgroups, stream, 0);
     TC_CUDA(cudaGetLastError());
     TC_CUDA(cudaStreamSynchronize(stream));
     std::string keys(size_t(nq) * TC_CAP * 8, '\0');
-    std::string cnts(size_t(nq) * 4, '\0');
     TC_CUDA(cudaMemcpy(&keys[0], s->cand, keys.size(), cudaMemcpyDeviceToHost));
-    TC_CUDA(cudaMemcpy(&cnts[0], s->cnt, cnts.size(), cudaMemcpyDeviceToHost));
     const uint64_t* kk = reinterpret_cast<const uint64_t*>(keys.data());
-    const unsigned* cc = reinterpret_cast<const unsigned*>(cnts.data());
     for (size_t i = 0; i < size_t(nq) * s->n_rows; ++i) out_host[i] = NAN;
     for (int q = 0; q < nq; ++q) {
-        const unsigned n = cc[q] < unsigned(TC_CAP) ? cc[q] : unsigned(TC_CAP);
-        for (unsigned i = 0; i < n; ++i) {
+        for (int64_t i = 0; i < s->n_tiles * TC_N; ++i) {
             const uint64_t key = kk[size_t(q) * TC_CAP + i];
             const int64_t row = key_id(key);
             if (row >= 0 && row < s->n_rows) out_host[size_t(q) * s->n_rows + row] = key_score(key);

@@ -3,10 +3,11 @@
 * ``shard_ranges``      -- contiguous row partition: shard g of G holds rows
   ``[g*ceil(N/G), min(N,(g+1)*ceil(N/G)))``; global id = local id + offset (the reference's
   ``I += i0``, dbsearch.py:238).
-* ``LocalEngine``       -- ONE process driving one handle per visible GPU (what the CLI user of
-  ``merizo.py search -d cuda`` gets): queries replicated, shards searched concurrently (one host
-  thread per device; ctypes drops the GIL), per-shard key lists copied peer-to-peer to the first
-  device and merged there by ``fcs_merge_topk``.
+* ``plan_shards``       -- how many GPUs a single-process database uses (one for CATH scale, all for TED scale).
+* ``LocalEngine``       -- ONE process, one host thread, one shard per chosen GPU (what the CLI user of
+  ``merizo.py search -d cuda`` gets): a mirror of the library's shard group (csrc/fcs_group.cu) -- queries
+  replicated, shards searched concurrently and asynchronously, per-shard key lists copied device-to-device
+  (NVLink peer copies) to the first GPU and merged there by K5.
 * ``DistributedEngine`` -- one process PER GPU under torchrun: each rank owns one shard; the
   per-rank ``[nq,k]`` packed key lists are exchanged with a single NCCL all-gather (8 bytes per
   entry over NVLink) and merged on every rank by the same kernel.  The key exchange is the only
@@ -20,7 +21,6 @@ torch is used for device memory, streams and torch.distributed only.
 """
 from __future__ import annotations
 
-from concurrent.futures import ThreadPoolExecutor
 from typing import Callable, Iterable, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -39,6 +39,8 @@ def shard_ranges(n_rows: int, n_shards: int) -> List[Tuple[int, int]]:
 
 
 def encode_keys(scores: np.ndarray, ids: np.ndarray) -> np.ndarray:
+    """Host mirror of the library's packed sort key (fcs_common.cuh make_key): order-preserving score word << 32 |
+    (0xFFFFFFFF - id); key 0 = empty slot."""
     s = np.ascontiguousarray(scores, dtype=np.float32).view(np.uint32).astype(np.uint64)
     neg = (s & np.uint64(0x80000000)) != 0
     ordered = np.where(neg, (~s) & np.uint64(0xFFFFFFFF), s | np.uint64(0x80000000))
@@ -59,37 +61,69 @@ def decode_keys(keys: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
     return scores, ids
 
 
+# ---- how many GPUs a single-process database uses -------------------------------------------------------------
+MIN_ROWS_PER_SHARD = 4_000_000   # a shard below ~2 GB scans in < 0.3 ms: the key exchange + merge (~40 us) stops paying
+HBM_FILL = 0.80                  # fraction of a GPU's free memory a shard may take
+
+
+def plan_shards(n_rows: int, n_devices: int, bytes_per_row: int = 512, free_bytes: Optional[float] = None,
+                min_rows_per_shard: int = MIN_ROWS_PER_SHARD) -> int:
+    """Number of row shards (= GPUs) for a database of n_rows rows on a node with n_devices GPUs: as few as keep the
+    per-shard scan well above the cross-GPU exchange cost, as many as memory needs.  A CATH-scale database (500 k rows,
+    256 MB, 44 us per scan) stays on ONE GPU; the 365 M-row TED database takes all 8."""
+    if n_devices < 1:
+        raise ValueError("n_devices >= 1 required")
+    by_size = max(1, n_rows // max(1, min_rows_per_shard))
+    shards = min(n_devices, by_size)
+    if free_bytes:
+        need = -(-int(n_rows * bytes_per_row) // int(free_bytes * HBM_FILL))
+        if need > n_devices:
+            raise native.FcsError(native.ERR_NOMEM, f"{n_rows} rows x {bytes_per_row} B do not fit {n_devices} GPUs "
+                                                    f"({free_bytes / 1e9:.0f} GB free each)")
+        shards = max(shards, need)
+    return max(1, min(shards, max(1, n_rows)))
+
+
 class LocalEngine:
-    """All visible GPUs (or ``devices``) from one process.  Rows are fed block by block."""
+    """All visible GPUs (or ``devices``) from ONE process and ONE host thread: a thin mirror of the library's shard
+    group (``fcs_group``, csrc/fcs_group.cu).  Queries are replicated, every shard searches on its own GPU and stream,
+    the per-shard key lists are copied device-to-device (NVLink) to the first GPU and merged there; the host sees one
+    synchronisation per search.  ``devices`` may repeat an ordinal (several shards on one GPU: the exchange + merge
+    path on a single-GPU box).  Rows are fed block by block; every shard is fed by its own loader thread."""
 
     def __init__(self, n_rows: int, devices: Optional[Sequence[int]] = None, normalise_rows: bool = False,
-                 keep_bf16: bool = False, has_lengths: bool = False):
+                 keep_bf16: bool = False, has_lengths: bool = False, n_shards: Optional[int] = None):
         if devices is None:
-            devices = list(range(native.device_count()))
+            visible = native.device_count()
+            if visible == 0:
+                raise native.FcsError(native.ERR_CUDA, "no CUDA device visible")
+            if n_shards is None:
+                n_shards = plan_shards(int(n_rows), visible, 512 + (256 if keep_bf16 else 0) + (2 if has_lengths else 0),
+                                       _free_bytes_per_gpu())
+            devices = list(range(min(visible, n_shards)))
+        devices = list(devices)
         if len(devices) == 0:
-            raise native.FcsError(native.ERR_CUDA, "no CUDA device visible")
-        # never more shards than 64-row tiles: tiny databases stay on one GPU
-        max_shards = max(1, n_rows // 4096)
-        devices = list(devices)[:max_shards]
+            raise native.FcsError(native.ERR_CUDA, "no CUDA device given")
+        devices = devices[:max(1, min(len(devices), int(n_rows)))]
         self.n_rows = int(n_rows)
         self.devices = devices
-        self.ranges = shard_ranges(self.n_rows, len(devices))
         self.has_lengths = has_lengths
-        self.shards: List[native.Database] = []
-        for dev, (r0, r1) in zip(devices, self.ranges):
-            self.shards.append(native.Database(r1 - r0, device=dev, id_offset=r0, normalise_rows=normalise_rows,
-                                               keep_bf16=keep_bf16, has_lengths=has_lengths))
-        self._pool = ThreadPoolExecutor(max_workers=len(devices)) if len(devices) > 1 else None
-        self._finalized = False
+        self.group = native.Group(self.n_rows, devices, normalise_rows=normalise_rows, keep_bf16=keep_bf16, has_lengths=has_lengths)
+        self.ranges = list(self.group.ranges)
+        assert self.ranges == shard_ranges(self.n_rows, len(devices))
+
+    @property
+    def n_shards(self) -> int:
+        return len(self.devices)
+
+    def shard(self, index: int) -> native.Database:
+        """Borrowed handle of one shard (timing / info)."""
+        return self.group.shard(index)
 
     # -- loading -----------------------------------------------------------------------------
     def upload(self, row0: int, rows: np.ndarray, lengths: Optional[np.ndarray] = None) -> None:
-        """Rows [row0, row0+len(rows)) of the GLOBAL matrix; split across the shards that own them."""
-        n = rows.shape[0]
-        for sh, (r0, r1) in zip(self.shards, self.ranges):
-            lo, hi = max(row0, r0), min(row0 + n, r1)
-            if lo < hi:
-                sh.upload(lo - r0, rows[lo - row0:hi - row0], None if lengths is None else lengths[lo - row0:hi - row0])
+        """Rows [row0, row0+len(rows)) of the GLOBAL matrix; the library splits them across the shards that own them."""
+        self.group.upload(row0, rows, lengths)
 
     def upload_blocks(self, blocks: Iterable[np.ndarray], lengths: Optional[np.ndarray] = None,
                       progress: Optional[Callable[[int], None]] = None) -> None:
@@ -103,45 +137,36 @@ class LocalEngine:
         if i0 != self.n_rows:
             raise native.FcsError(native.ERR_INVALID, f"iterator yielded {i0} rows, database has {self.n_rows}")
 
+    def upload_file(self, path: str, file_offset: int = 0) -> None:
+        """The whole matrix from a file of headerless fp32 rows (the faiss flavour's *_raw_128d_norm.db, dbutil.py:28-30):
+        every shard reads its own byte range with positional reads from its own thread."""
+        self.group.upload_file(path, file_offset, 0, self.n_rows)
+
     def finalize(self) -> None:
-        for sh in self.shards:
-            sh.finalize()
-        self._finalized = True
+        self.group.finalize()
 
     # -- search ------------------------------------------------------------------------------
     def search(self, q: np.ndarray, k: int, qlen: Optional[np.ndarray] = None, mincov: float = 0.0,
                qnorm: int = native.QNORM_NONE, mode: int = native.MODE_AUTO, kprime: int = 0):
         """(scores f32 [nq,k], ids i64 [nq,k]) as host arrays; exact; global ids."""
-        q = np.ascontiguousarray(q, dtype=np.float32).reshape(-1, DIM)
-        if len(self.shards) == 1:
-            return self.shards[0].search(q, k, qlen=qlen, mincov=mincov, qnorm=qnorm, mode=mode, kprime=kprime)
-        futs = [self._pool.submit(sh.search, q, k, qlen, mincov, qnorm, mode, kprime) for sh in self.shards]
-        parts = [f.result() for f in futs]
-        keys = np.stack([encode_keys(s, i) for s, i in parts])  # [G, nq, k]
-        return self._merge(keys, k)
-
-    def _merge(self, keys: np.ndarray, k: int):
-        import torch
-
-        dev = torch.device("cuda", self.devices[0])
-        g, nq, _ = keys.shape
-        kd = torch.from_numpy(keys.view(np.int64)).to(dev)
-        sc = torch.empty((nq, k), dtype=torch.float32, device=dev)
-        ids = torch.empty((nq, k), dtype=torch.int64, device=dev)
-        st = torch.cuda.current_stream(dev)
-        native.merge_topk(self.devices[0], kd.data_ptr(), g, nq, k, sc.data_ptr(), ids.data_ptr(), stream=st.cuda_stream)
-        st.synchronize()
-        return sc.cpu().numpy(), ids.cpu().numpy()
+        return self.group.search(q, k, qlen=qlen, mincov=mincov, qnorm=qnorm, mode=mode, kprime=kprime)
 
     def close(self) -> None:
-        for sh in self.shards:
-            sh.close()
-        if self._pool:
-            self._pool.shutdown(wait=False)
-        self.shards = []
+        self.group.close()
 
     def __len__(self) -> int:
         return self.n_rows
+
+
+def _free_bytes_per_gpu() -> Optional[float]:
+    try:
+        import torch
+
+        if torch.cuda.is_available():
+            return float(min(torch.cuda.mem_get_info(d)[0] for d in range(torch.cuda.device_count())))
+    except Exception:
+        pass
+    return None
 
 
 class DistributedEngine:
@@ -167,11 +192,23 @@ class DistributedEngine:
         self.n_rows_global = int(n_rows_global)
         self.ranges = shard_ranges(self.n_rows_global, self.row_shards)
         self.row0, self.row1 = self.ranges[self.shard_index]
+        if device is None:
+            # one rank per GPU: the launcher's LOCAL_RANK names this rank's device; never default every rank to GPU 0
+            import os
+
+            if "LOCAL_RANK" in os.environ:
+                device = int(os.environ["LOCAL_RANK"])
+            elif self.world == 1:
+                device = 0
+            elif create_handle:
+                raise ValueError("DistributedEngine: pass device= (or launch with torchrun so that LOCAL_RANK is set)")
         self.device = device
         self._side = None
+        self._pinned = None
+        self._last_keys = None
         self.db: Optional[native.Database] = None
         if create_handle:
-            self.db = native.Database(self.row1 - self.row0, device=device or 0, id_offset=self.row0,
+            self.db = native.Database(self.row1 - self.row0, device=self.device, id_offset=self.row0,
                                       normalise_rows=normalise_rows, keep_bf16=keep_bf16, has_lengths=has_lengths)
 
     @staticmethod
@@ -183,6 +220,12 @@ class DistributedEngine:
                 best = q
         return best
 
+    @property
+    def dev_index(self) -> int:
+        if self.device is None:
+            raise ValueError("DistributedEngine: no device was given for this rank")
+        return int(self.device)
+
     def query_slice(self, nq: int) -> Tuple[int, int, int]:
         """(first query, one-past-last, padded slice length) of this rank's query group."""
         per = -(-nq // self.q_groups)
@@ -193,7 +236,7 @@ class DistributedEngine:
         """This rank's [nq,k] packed keys (torch int64 CUDA tensor viewing uint64 keys)."""
         import torch
 
-        dev = torch.device("cuda", self.device or 0)
+        dev = torch.device("cuda", self.dev_index)
         keys = torch.zeros((nq, k), dtype=torch.int64, device=dev)
         cur = torch.cuda.current_stream(dev)
         if cur.cuda_stream != 0:
@@ -210,20 +253,51 @@ class DistributedEngine:
         return keys
 
     def search_host(self, q_host, k: int, **kw):
-        """Host arrays in (the same queries on every rank), host arrays out: H2D copy, shard search, NCCL key
-        all-gather, GPU merge, D2H copy.  This is the end-to-end call of the one-rank-per-GPU deployment."""
+        """Host arrays in (the same queries on every rank), host arrays out: H2D copy from pinned memory, shard search,
+        NCCL key all-gather, GPU merge, D2H copy into pinned memory -- one host synchronisation.  This is the end-to-end
+        call of the one-rank-per-GPU deployment.  Exact on every rank: if some rank had to defer part of its exact-scan
+        fallback queue (more than ASYNC_FALLBACK_QUERIES queries failed their certificate), all ranks learn it through a
+        one-word all-reduce and the exchange + merge is repeated."""
         import torch
+        import torch.distributed as dist
 
-        dev = torch.device("cuda", self.device or 0)
+        dev = torch.device("cuda", self.dev_index)
         qh = torch.as_tensor(q_host, dtype=torch.float32).reshape(-1, DIM)
-        if not qh.is_pinned():
-            qh = qh.pin_memory()
-        q_dev = qh.to(dev, non_blocking=True)
-        sc, ids = self.search(q_dev, k, **kw)
-        return sc.cpu().numpy(), ids.cpu().numpy()
+        nq = qh.shape[0]
+        pin = self._pinned
+        if pin is None or pin["q"].shape[0] < nq or pin["k"] != k:
+            pin = self._pinned = {"q": torch.empty((nq, DIM), dtype=torch.float32).pin_memory(), "k": k,
+                                  "sc": torch.empty((nq, k), dtype=torch.float32).pin_memory(),
+                                  "ids": torch.empty((nq, k), dtype=torch.int64).pin_memory(),
+                                  "flag": torch.zeros(1, dtype=torch.int32, device=dev)}
+        if qh.is_pinned():
+            src = qh
+        else:
+            pin["q"][:nq].copy_(qh)
+            src = pin["q"][:nq]
+        q_dev = src.to(dev, non_blocking=True)
+        cur = torch.cuda.current_stream(dev)
+        for attempt in range(2):
+            sc, ids = self.search(q_dev, k, **kw)
+            pin["sc"][:nq].copy_(sc, non_blocking=True)
+            pin["ids"][:nq].copy_(ids, non_blocking=True)
+            cur.synchronize()
+            deferred = 0
+            if self.db is not None:
+                deferred = 1 if self.db.search_finish(cur.cuda_stream) > native.ASYNC_FALLBACK_QUERIES else 0
+            if self.world > 1 and dist.is_initialized():
+                pin["flag"].fill_(deferred)
+                dist.all_reduce(pin["flag"], op=dist.ReduceOp.MAX)
+                deferred = int(pin["flag"].item())
+            if not deferred:
+                break
+            # the finished shard lists are in place now: a second pass re-runs the (idempotent) exchange on complete lists
+            kw = dict(kw, _reuse_local=True)
+        return pin["sc"][:nq].numpy().copy(), pin["ids"][:nq].numpy().copy()
 
-    def search(self, q_dev, k: int, local_search=None, merge=None, qlen=None, **kw):
-        """Replicated queries in, identical (scores, ids) on every rank out (torch tensors)."""
+    def search(self, q_dev, k: int, local_search=None, merge=None, qlen=None, _reuse_local=False, **kw):
+        """Replicated queries in, identical (scores, ids) on every rank out (torch tensors).  Asynchronous on the current
+        stream: nothing here waits for the host."""
         import torch
         import torch.distributed as dist
 
@@ -231,13 +305,16 @@ class DistributedEngine:
         lo, hi, per = self.query_slice(nq)
         q_mine = q_dev[lo:hi]
         ql_mine = None if qlen is None else np.asarray(qlen)[lo:hi]
-        if hi - lo > 0:
+        if _reuse_local and self._last_keys is not None:
+            keys = self._last_keys  # the previous call's shard list, completed in place by search_finish
+        elif hi - lo > 0:
             if local_search:
                 keys = local_search(q_mine, hi - lo, k)
             else:
                 keys = self.local_keys(q_mine, hi - lo, k, qlen=ql_mine, **kw)
         else:
             keys = torch.zeros((0, k), dtype=torch.int64, device=q_dev.device)
+        self._last_keys = keys
         if hi - lo < per:  # pad the slice: every rank contributes the same shape; key 0 = empty
             pad = torch.zeros((per - (hi - lo), k), dtype=torch.int64, device=keys.device)
             keys = torch.cat([keys, pad], dim=0)
@@ -252,7 +329,7 @@ class DistributedEngine:
             sc = torch.empty((self.q_groups * per, k), dtype=torch.float32, device=keys.device)
             ids = torch.empty((self.q_groups * per, k), dtype=torch.int64, device=keys.device)
             st = torch.cuda.current_stream(keys.device)
-            native.merge_topk(self.device or 0, lists.data_ptr(), self.row_shards, self.q_groups * per, k, sc.data_ptr(),
+            native.merge_topk(self.dev_index, lists.data_ptr(), self.row_shards, self.q_groups * per, k, sc.data_ptr(),
                               ids.data_ptr(), stream=st.cuda_stream)
         return sc[:nq], ids[:nq]
 

@@ -166,13 +166,12 @@ def dbsearch_faiss(queries: list, target_dict: dict, tmp: str, network, topk: in
     else:
         pdb_chains = ["A"] * nq
 
-    # resident, row-sharded database: uploaded once per process and path
-    key = (os.path.abspath(dbfname), "faiss")
-    resident = _dbs._RESIDENT.get(key)
-    if resident is None:
-        emb = embedding_memmap(dbfname, int(dbinfo["DB_SIZE"]), int(dbinfo["DB_DIM"]))
-        logger.info("DB iterator using batchsize of " + str(search_batchsize))
-        resident = _dbs.load_resident(row_blocks(emb, int(search_batchsize)), emb.shape[0], key)
+    # resident, row-sharded database: read from the file once per process (and per version of the file) by the native
+    # loader -- one reader thread per GPU, positional reads into pinned staging (dbutil.py:28-35 pages it in per search)
+    if int(dbinfo["DB_DIM"]) != native.DIM:
+        logger.error("DB_DIM %s is not supported (FoldClassNet embeddings are %d-d)" % (dbinfo["DB_DIM"], native.DIM))
+        sys.exit(1)
+    resident = _dbs.load_resident_file(dbfname, int(dbinfo["DB_SIZE"]), device)
 
     query_dicts, q_emb = embed_queries(queries, network, device, inputs_are_ca, pdb_chains)
 

@@ -26,7 +26,10 @@ EMBED_MODE_FP32, EMBED_MODE_TC = 0, 1
 EXPORTS = [
     "fcs_version", "fcs_last_error", "fcs_device_count", "fcs_db_create", "fcs_db_upload",
     "fcs_db_upload_device", "fcs_db_finalize", "fcs_db_get_info", "fcs_db_destroy", "fcs_search",
-    "fcs_search_device", "fcs_merge_topk", "fcs_get_timing", "fcs_set_profiling", "fcs_debug_tc_approx",
+    "fcs_search_device", "fcs_search_finish", "fcs_merge_topk", "fcs_get_timing", "fcs_set_profiling", "fcs_debug_tc_approx",
+    "fcs_debug_tc_plan", "fcs_debug_tc_tile_of", "fcs_db_upload_file",
+    "fcs_group_create", "fcs_group_upload", "fcs_group_upload_file", "fcs_group_finalize", "fcs_group_search",
+    "fcs_group_get_info", "fcs_group_shard", "fcs_group_last_fallbacks", "fcs_group_destroy",
     # include/fcsembed.h
     "fcs_embedder_create", "fcs_embedder_destroy", "fcs_embed", "fcs_embed_to_device", "fcs_embed_get_timing",
     "fcs_embed_debug_layer", "fcs_embed_set_mode",
@@ -88,11 +91,24 @@ def load() -> C.CDLL:
     lib.fcs_db_create.argtypes = [i32, i64, i32, i64, u32, C.POINTER(vp)]
     lib.fcs_db_upload.argtypes = [vp, i64, i64, vp, vp]
     lib.fcs_db_upload_device.argtypes = [vp, i64, i64, vp, vp]
+    lib.fcs_db_upload_file.argtypes = [vp, i64, i64, C.c_char_p, i64]
+    lib.fcs_group_create.argtypes = [C.POINTER(C.c_int), i32, i64, i32, u32, C.POINTER(vp)]
+    lib.fcs_group_upload.argtypes = [vp, i64, i64, vp, vp]
+    lib.fcs_group_upload_file.argtypes = [vp, C.c_char_p, i64, i64, i64]
+    lib.fcs_group_finalize.argtypes = [vp]
+    lib.fcs_group_search.argtypes = [vp, vp, i32, vp, f32, i32, i32, i32, i32, vp, vp]
+    lib.fcs_group_get_info.argtypes = [vp, C.POINTER(C.c_int), vp, vp, i32]
+    lib.fcs_group_shard.argtypes = [vp, i32, C.POINTER(vp)]
+    lib.fcs_group_last_fallbacks.argtypes = [vp]
+    lib.fcs_group_destroy.argtypes = [vp]
     lib.fcs_db_finalize.argtypes = [vp]
     lib.fcs_db_get_info.argtypes = [vp, C.POINTER(Info)]
     lib.fcs_db_destroy.argtypes = [vp]
     lib.fcs_search.argtypes = [vp, vp, i32, vp, f32, i32, i32, i32, i32, vp, vp]
     lib.fcs_search_device.argtypes = [vp, vp, i32, vp, f32, i32, i32, i32, i32, vp, vp, vp, vp]
+    lib.fcs_search_finish.argtypes = [vp, vp, C.POINTER(C.c_int)]
+    lib.fcs_debug_tc_plan.argtypes = [i64, i32, vp, i32]
+    lib.fcs_debug_tc_tile_of.argtypes = [i64, i64, i64, i64]
     lib.fcs_merge_topk.argtypes = [i32, vp, i32, i32, i32, vp, vp, vp]
     lib.fcs_get_timing.argtypes = [vp, C.POINTER(Timing)]
     lib.fcs_debug_tc_approx.argtypes = [vp, vp, i32, i32, vp]
@@ -108,6 +124,7 @@ def load() -> C.CDLL:
         if name not in ("fcs_last_error",):
             getattr(lib, name).restype = C.c_int
     lib.fcs_last_error.restype = C.c_char_p
+    lib.fcs_debug_tc_tile_of.restype = C.c_int64
     _lib = lib
     return lib
 
@@ -150,6 +167,10 @@ class Database:
             raise FcsError(ERR_INVALID, "lengths and rows disagree on the row count")
         _check(self._lib.fcs_db_upload(self._h, int(row0), rows.shape[0], _np_ptr(rows), _np_ptr(lens)))
 
+    def upload_file(self, row0: int, n: int, path: str, file_offset: int = 0) -> None:
+        """Rows [row0, row0+n) from a file of headerless fp32 rows, starting at byte `file_offset`."""
+        _check(self._lib.fcs_db_upload_file(self._h, int(row0), int(n), os.fsencode(path), int(file_offset)))
+
     def upload_device(self, row0: int, n: int, rows_ptr: int, lengths_ptr: Optional[int] = None) -> None:
         _check(self._lib.fcs_db_upload_device(self._h, int(row0), int(n), C.c_void_p(rows_ptr),
                                               C.c_void_p(lengths_ptr) if lengths_ptr else None))
@@ -182,6 +203,13 @@ class Database:
             C.c_void_p(out_scores_ptr) if out_scores_ptr else None, C.c_void_p(out_ids_ptr) if out_ids_ptr else None,
             C.c_void_p(out_keys_ptr) if out_keys_ptr else None, C.c_void_p(stream) if stream else None))
 
+    def search_finish(self, stream: int = 0) -> int:
+        """Synchronise `stream` and complete whatever the last asynchronous tensor-core search deferred (a fallback
+        queue longer than FCS_ASYNC_FALLBACK_QUERIES); returns the length of that queue."""
+        n = C.c_int(0)
+        _check(self._lib.fcs_search_finish(self._h, C.c_void_p(stream) if stream else None, C.byref(n)))
+        return n.value
+
     def debug_tc_approx(self, q: np.ndarray, qnorm: int = QNORM_NONE) -> np.ndarray:
         """Test hook: bf16 tensor-core scores [nq, n_rows] (shards of <= 4096 rows)."""
         q = np.ascontiguousarray(q, dtype=np.float32).reshape(-1, DIM)
@@ -212,6 +240,104 @@ class Database:
             self.close()
         except Exception:
             pass
+
+
+class _BorrowedShard(Database):
+    """A shard handle owned by a Group (timing / info only; never destroyed from here)."""
+
+    def __init__(self, lib, handle, n_rows, device, id_offset, flags):
+        self._lib, self._h = lib, handle
+        self.n_rows, self.device, self.id_offset, self.flags = n_rows, device, id_offset, flags
+        self.has_lengths = bool(flags & DB_HAS_LENGTHS)
+
+    def close(self) -> None:
+        self._h = C.c_void_p()
+
+
+class Group:
+    """Several row shards behind one handle (fcs_group): one host thread drives all of them; key lists are exchanged
+    device-to-device and merged on the first GPU.  `devices[s]` = GPU of shard s (ordinals may repeat)."""
+
+    def __init__(self, n_rows: int, devices, normalise_rows: bool = False, keep_bf16: bool = False, has_lengths: bool = False):
+        self._lib = load()
+        self._h = C.c_void_p()
+        devices = [int(d) for d in devices]
+        flags = (DB_NORMALISE_ROWS if normalise_rows else 0) | (DB_KEEP_BF16 if keep_bf16 else 0) | \
+                (DB_HAS_LENGTHS if has_lengths else 0)
+        arr = (C.c_int * len(devices))(*devices)
+        _check(self._lib.fcs_group_create(arr, len(devices), int(n_rows), DIM, flags, C.byref(self._h)))
+        self.n_rows, self.devices, self.flags = int(n_rows), devices, flags
+        bounds = np.zeros(len(devices) + 1, dtype=np.int64)
+        n = C.c_int(0)
+        _check(self._lib.fcs_group_get_info(self._h, C.byref(n), _np_ptr(bounds), None, len(devices)))
+        self.bounds = [int(b) for b in bounds]
+        self.ranges = [(self.bounds[i], self.bounds[i + 1]) for i in range(len(devices))]
+
+    def shard(self, index: int) -> Database:
+        h = C.c_void_p()
+        _check(self._lib.fcs_group_shard(self._h, int(index), C.byref(h)))
+        r0, r1 = self.ranges[index]
+        return _BorrowedShard(self._lib, h, r1 - r0, self.devices[index], r0, self.flags)
+
+    def upload(self, row0: int, rows: np.ndarray, lengths: Optional[np.ndarray] = None) -> None:
+        rows = np.ascontiguousarray(rows, dtype=np.float32)
+        if rows.ndim != 2 or rows.shape[1] != DIM:
+            raise FcsError(ERR_INVALID, f"rows must be [n,{DIM}] float32, got {rows.shape}")
+        lens = None if lengths is None else np.ascontiguousarray(lengths, dtype=np.int32)
+        if lens is not None and lens.shape[0] != rows.shape[0]:
+            raise FcsError(ERR_INVALID, "lengths and rows disagree on the row count")
+        _check(self._lib.fcs_group_upload(self._h, int(row0), rows.shape[0], _np_ptr(rows), _np_ptr(lens)))
+
+    def upload_file(self, path: str, file_offset: int, row0: int, n: int) -> None:
+        _check(self._lib.fcs_group_upload_file(self._h, os.fsencode(path), int(file_offset), int(row0), int(n)))
+
+    def finalize(self) -> None:
+        _check(self._lib.fcs_group_finalize(self._h))
+
+    def search(self, q: np.ndarray, k: int, qlen: Optional[np.ndarray] = None, mincov: float = 0.0,
+               qnorm: int = QNORM_NONE, mode: int = MODE_AUTO, kprime: int = 0):
+        q = np.ascontiguousarray(q, dtype=np.float32).reshape(-1, DIM)
+        nq = q.shape[0]
+        ql = None if qlen is None else np.ascontiguousarray(qlen, dtype=np.int32).reshape(-1)
+        if ql is not None and ql.shape[0] != nq:
+            raise FcsError(ERR_INVALID, "qlen must have one entry per query")
+        scores = np.empty((nq, int(k)), dtype=np.float32)
+        ids = np.empty((nq, int(k)), dtype=np.int64)
+        _check(self._lib.fcs_group_search(self._h, _np_ptr(q), nq, _np_ptr(ql), float(mincov), int(k), int(qnorm), int(mode),
+                                          int(kprime), _np_ptr(scores), _np_ptr(ids)))
+        return scores, ids
+
+    def last_fallbacks(self) -> int:
+        return int(self._lib.fcs_group_last_fallbacks(self._h))
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.fcs_group_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+ASYNC_FALLBACK_QUERIES = 32
+
+TC_PLAN_FIELDS = ("tiles", "j0", "stride", "comp_t", "first", "rank", "partition")
+
+
+def debug_tc_plan(n_rows: int, kprime: int = 0, max_rounds: int = 16):
+    """Test hook: the rounds the tensor-core path runs for a shard of n_rows rows (list of dicts, TC_PLAN_FIELDS)."""
+    out = np.zeros((max_rounds, len(TC_PLAN_FIELDS)), dtype=np.int64)
+    n = load().fcs_debug_tc_plan(int(n_rows), int(kprime), _np_ptr(out), int(max_rounds))
+    if n < 0:
+        _check(n)
+    return [dict(zip(TC_PLAN_FIELDS, (int(v) for v in out[i]))) for i in range(n)]
+
+
+def debug_tc_tile_of(j0: int, stride: int, comp_t: int, idx: int) -> int:
+    return int(load().fcs_debug_tc_tile_of(int(j0), int(stride), int(comp_t), int(idx)))
 
 
 def merge_topk(device: int, keys_ptr: int, n_lists: int, nq: int, k: int, out_scores_ptr: int, out_ids_ptr: int,

@@ -83,3 +83,32 @@ def test_record_files_vectorised_readers(tiny_faiss_db):
     for got, i in zip(rec.coords(ids), ids):
         np.testing.assert_array_equal(got, coords[i])
     assert rec.has_metadata()
+
+
+def test_plan_shards_small_databases_stay_on_one_gpu():
+    """CATH scale (500 k rows) must not be spread over 8 GPUs for a 44 us scan; TED scale needs all of them."""
+    assert engine.plan_shards(14_942, 8) == 1
+    assert engine.plan_shards(500_000, 8) == 1
+    assert engine.plan_shards(10_000_000, 8) == 2
+    assert engine.plan_shards(365_000_000, 8) == 8
+    assert engine.plan_shards(365_000_000, 8, bytes_per_row=768, free_bytes=170e9) == 8
+    # memory forces more shards than the size rule asks for
+    assert engine.plan_shards(6_000_000, 8, bytes_per_row=768, free_bytes=2e9) == 3
+    with pytest.raises(Exception):
+        engine.plan_shards(365_000_000, 1, bytes_per_row=768, free_bytes=170e9)
+
+
+def test_tc_round_plan_visits_every_tile_exactly_once():
+    """The tensor-core path's sampled rounds + complement sweep partition the shard's tiles (host mirror of tile_of)."""
+    from merizo_search_b200 import native
+
+    for n_rows in (1, 100, 4096, 4097, 5000, 8191, 8192, 70001, 300000, 1_250_000, 3_333_333):
+        for kp in (64, 160, 512):
+            plan = native.debug_tc_plan(n_rows, kp)
+            nt = (n_rows + 127) // 128
+            seen = []
+            for r in plan:
+                seen += [native.debug_tc_tile_of(r["j0"], r["stride"], r["comp_t"], i) for i in range(r["tiles"])]
+            assert sorted(seen) == list(range(nt)), (n_rows, kp, plan)
+            assert plan[0]["first"] == 1 and plan[0]["tiles"] * 128 <= 4096 and plan[-1]["partition"] == 1 and plan[-1]["rank"] == kp
+            assert all(1 <= r["rank"] <= 1024 for r in plan[:-1])

@@ -40,6 +40,22 @@ def test_install_replaces_the_hot_path_callables(ref_module):
     assert "search_query_against_db(" in inspect.getsource(ref_module.dbsearch)
 
 
+def test_install_rebinds_modules_that_star_imported_the_originals(ref_module):
+    """dbsearch_fulllength.py:29 does `from .dbsearch import *` and merizo.py:15 imports it at start-up, i.e. BEFORE
+    install() can run: multi_domain_search (dbsearch_fulllength.py:303) must still get the resident database."""
+    from merizo_search_b200 import dbsearch as b200
+    from merizo_search_b200 import faiss_driver
+
+    full = importlib.import_module("programs.Foldclass.dbsearch_fulllength")  # imported first, like merizo.py does
+    assert full.read_database is ref_module.read_database
+    b200.install(ref_module)
+    assert full.read_database is b200.read_database
+    assert full.search_query_against_db is b200.search_query_against_db
+    assert full.dbsearch_faiss is faiss_driver.dbsearch_faiss
+    assert full.network_setup is ref_module.network_setup and hasattr(full.network_setup, "__wrapped__")
+    assert "read_database(" in inspect.getsource(full.multi_domain_search)
+
+
 def test_replacements_keep_the_reference_signatures(ref_module):
     from merizo_search_b200 import dbsearch as b200
     from merizo_search_b200 import faiss_driver
@@ -143,8 +159,8 @@ def test_reference_dbsearch_driver_gives_the_same_hits_with_the_spliced_path(ref
     np.asarray(idx, dtype=np.int64).tofile(base + ".metadata.index")
     query = {"name": "/q/query.pdb", "coords": (chains[3] + 0.05).astype(np.float32), "seq": "A" * lens[3]}
 
-    def run():
-        target = ref_module.read_database(base, torch.device("cpu"))
+    def run(read_device="cpu"):
+        target = ref_module.read_database(base, torch.device(read_device))
         return ref_module.dbsearch(dict(query), target, str(tmp_path), net, 5, 0.7, 0.5, 0.5, False, torch.device("cpu"),
                                    inputs_are_ca=True, skip_tmalign=True)
 
@@ -152,7 +168,9 @@ def test_reference_dbsearch_driver_gives_the_same_hits_with_the_spliced_path(ref
     monkeypatch.setattr(b200, "LocalEngine", _OraclePtEngine)
     b200._RESIDENT.clear()
     b200.install(ref_module)
-    got, _ = run()                                    # the same driver, hot path spliced
+    with pytest.raises(b200.native.FcsError):          # the spliced path has no CPU implementation and says so
+        run()
+    got, _ = run("cuda")                              # the same driver, hot path spliced (engine stubbed: no GPU touched)
     b200._RESIDENT.clear()
     assert len(want) >= 2 and list(got.keys()) == list(want.keys())
     for key in want:

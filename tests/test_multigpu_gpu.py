@@ -25,7 +25,7 @@ def test_local_engine_two_shards_equals_oracle(n, nq, k, mode):
     db = synth.host_db(n, base_seed=81)
     q = synth.host_queries(nq, 81, normalise=True)
     eng = engine.LocalEngine(n, devices=[0, 1], keep_bf16=(mode == native.MODE_TC))
-    assert len(eng.shards) == 2 and eng.ranges == engine.shard_ranges(n, 2)
+    assert eng.n_shards == 2 and eng.ranges == engine.shard_ranges(n, 2)
     eng.upload_blocks(orc.db_iterator(db, 7777))
     eng.finalize()
     s, i = eng.search(q, k, mode=mode)
