@@ -58,6 +58,35 @@ EMBED_WORKLOAD = dict(n=2048, len_seed=21, chain_seed=3, weight_seed=2024,
                            "(25..683, mean 126), seeded stand-in weights; fused edge kernel (tcgen05, or fp32 with FCS_EMBED_MODE=0)")
 
 
+def make_config(wl, wl_name, rows_total, n_local, world, n_shards, qg, nq_local, extra=None):
+    """The `config` object of the JSON line: identical keys for the GPU arm and the reference arm."""
+    cfg = {"workload": wl_name, "description": wl["desc"], "rows_total": rows_total, "rows_per_gpu": n_local,
+           "nq": wl["nq"], "k": wl["k"], "path": wl["mode"], "coverage_mask": wl["mask"],
+           "l2": "inputs larger than L2 (database streamed from HBM every step)",
+           "parallelism": (f"{n_shards} row shard(s) x {qg} query group(s) over {world} ranks, one NCCL all-gather of "
+                           "packed keys + GPU merge") if world > 1 else "single GPU",
+           "queries_per_gpu": nq_local}
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+def layout(wl, rows_total, world, query_groups):
+    """(query groups, row shards) of the N-rank layout bench.py uses for a workload (engine.DistributedEngine)."""
+    from merizo_search_b200.engine import DistributedEngine
+
+    qg = query_groups
+    if world == 1:
+        qg = 1
+    elif wl["scaling"] == "weak":
+        qg = 1  # the TED-scale slices are the row-sharded configuration of the metric: never replicate them
+    elif qg <= 0:
+        qg = DistributedEngine.auto_query_groups(rows_total, world, bytes_per_row=514 + (256 if wl["mode"] == "tc" else 0))
+    while qg > 1 and (world % qg != 0 or qg > wl["nq"]):
+        qg -= 1
+    return qg, world // qg
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -154,6 +183,36 @@ def cpu_oracle_throughput(wl, n_rows_total, budget_s=12.0):
     nq_s = min(nq, 4096)
     db = synth.host_db(n, base_seed=1)
     q = synth.host_queries(nq_s, 5, normalise=True)
+    try:  # faiss itself when the box has it (it is not in this image: un-vendored dependency)
+        import faiss  # noqa: F401
+    except Exception:
+        faiss = None
+    if faiss is not None:
+        faiss.omp_set_num_threads(cores)
+
+        def faiss_pass():  # the reference's knn_exact_faiss loop (dbsearch.py:213-248): IndexFlat per block + ResultHeap
+            rh = faiss.ResultHeap(nq_s, k, keep_max=True)
+            for i0 in range(0, n, 262_144):
+                xb = db[i0:i0 + 262_144]
+                index = faiss.IndexFlat(128, faiss.METRIC_INNER_PRODUCT)
+                index.add(xb)
+                D, I = index.search(q, k)
+                I += i0
+                rh.add_result(D, I)
+            rh.finalize()
+            return rh.D, rh.I
+
+        faiss_pass()
+        t0, reps = time.perf_counter(), 0
+        while True:
+            faiss_pass()
+            reps += 1
+            if time.perf_counter() - t0 > budget_s * 0.5 or reps >= 20:
+                break
+        dt = (time.perf_counter() - t0) / reps
+        qps = nq_s / dt * (n / n_rows_total)
+        return qps, cores, (f"{nq_s} queries x {n} rows (of {n_rows_total}), faiss-cpu {faiss.__version__} IndexFlat(IP) + ResultHeap in the "
+                            f"reference's block loop (262144-row blocks), {dt:.2f} s/pass x {reps}, extrapolated linearly in rows")
     orc.knn_exact_blockwise(q[: min(nq_s, 64)], orc.db_iterator(db[:65536], 65536), k)  # warm
     t0 = time.perf_counter()
     reps = 0
@@ -267,6 +326,233 @@ def run_embed(args, steps=3, warmup=3, cpu_baseline=True):
     return out
 
 
+# --------------------------------------------------------------------------------------------- loader
+def run_loader(args, rows=4_000_000):
+    """Host -> HBM rate of the database loader (read_dbinfo/db_memmap/db_iterator, loaded ONCE here):
+    a file of headerless fp32 rows (the faiss flavour's layout, dbutil.py:28-30) through (a) the native file loader
+    (positional reads into pinned staging, one reader thread per shard) and (b) the block iterator over a numpy memmap
+    (the reference's db_iterator blocks of 262144 rows fed to fcs_group_upload).  2 GB; the file sits in the page cache."""
+    import tempfile
+
+    from merizo_search_b200 import engine, synth
+
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    tmpdir = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else tempfile.gettempdir()
+    path = os.path.join(tmpdir, f"fcs_loader_bench_{os.getpid()}.db")
+    blk = 1 << 18
+    try:
+        with open(path, "wb") as fh:
+            for b in range(0, rows, blk):
+                synth.host_db(min(blk, rows - b), base_seed=77 + b // blk).tofile(fh)
+        nbytes = rows * 512
+        out = {"rows": rows, "bytes": nbytes, "file": f"{tmpdir} (page cache)", "shards": 1}
+        for name in ("file", "memmap_blocks"):
+            best = None
+            for _ in range(2):
+                eng = engine.LocalEngine(rows, devices=[local_rank], keep_bf16=False)
+                t0 = time.perf_counter()
+                if name == "file":
+                    eng.upload_file(path)
+                else:
+                    mm = np.memmap(path, dtype=np.float32, mode="r", shape=(rows, 128))
+                    eng.upload_blocks(mm[i0:i0 + 262_144] for i0 in range(0, rows, 262_144))
+                eng.finalize()
+                dt = time.perf_counter() - t0
+                eng.close()
+                best = dt if best is None else min(best, dt)
+            out[name + "_gbs"] = nbytes / best / 1e9
+            out[name + "_s"] = best
+        out["api"] = ("file: LocalEngine.upload_file -> fcs_group_upload_file (pread into pinned staging, H2D DMA double-buffered); "
+                      "memmap_blocks: LocalEngine.upload_blocks over np.memmap -> fcs_group_upload (page-cache copy into pinned staging)")
+        return out
+    finally:
+        try:
+            os.unlink(path)
+        except OSError:
+            pass
+
+
+# --------------------------------------------------------------------------------------------- single-process engine
+def run_local(args):
+    """`--workload local`: the single-process deployment (what `merizo.py search -d cuda` gets): engine.LocalEngine = the
+    library's shard group over ALL visible GPUs, driven by one host thread, key lists exchanged device-to-device.  Wall-clock
+    latency per call through the host-buffer API for the CATH-scale and the TED-scale databases, with a brute-force check."""
+    import torch
+
+    from merizo_search_b200 import engine, native, synth
+
+    ngpu = torch.cuda.device_count()
+    blk = 1 << 20
+    res = {"gpus_visible": ngpu, "cases": []}
+
+    def build(rows_total, devices, mask, keep_bf16):
+        eng = engine.LocalEngine(rows_total, devices=devices, keep_bf16=keep_bf16, has_lengths=mask)
+        lens_all = synth.host_lengths(rows_total).astype(np.int32) if mask else None
+        for si, (r0, r1) in enumerate(eng.ranges):
+            dev = torch.device("cuda", eng.devices[si])
+            sh = eng.shard(si)
+            with torch.cuda.device(dev):
+                ld = torch.from_numpy(lens_all[r0:r1]).to(dev) if mask else None
+                b0 = r0
+                while b0 < r1:  # global 2^20-row blocks (the same block seeds as every other bench workload)
+                    gb = b0 // blk
+                    x = synth.device_block(gb, min(blk, rows_total - gb * blk), dev, base_seed=1000)
+                    lo, hi = b0 - gb * blk, min(r1, (gb + 1) * blk) - gb * blk
+                    part = x[lo:hi].contiguous()
+                    sh.upload_device(b0 - r0, hi - lo, part.data_ptr(), ld[b0 - r0:b0 - r0 + hi - lo].contiguous().data_ptr() if mask else None)
+                    b0 += hi - lo
+                    del x, part
+                torch.cuda.synchronize(dev)
+        eng.finalize()
+        return eng, lens_all
+
+    def brute(rows_total, q, k, mask, lens_all):
+        dev = torch.device("cuda", 0)
+        qd = torch.from_numpy(q).to(dev)
+        best_s = torch.full((q.shape[0], k), -float("inf"), device=dev)
+        best_i = torch.full((q.shape[0], k), -1, dtype=torch.int64, device=dev)
+        for b0 in range(0, rows_total, blk):
+            nb = min(blk, rows_total - b0)
+            x = synth.device_block(b0 // blk, nb, dev, base_seed=1000)
+            sc = qd @ x.T
+            if mask:
+                need = torch.from_numpy(lens_all[b0:b0 + nb]).to(dev).to(torch.float32) * torch.tensor(0.7, dtype=torch.float32, device=dev)
+                sc = sc * (torch.tensor(150.0, device=dev) >= need).to(torch.float32)[None, :]
+            ts, ti = torch.topk(sc, min(k, nb), dim=1)
+            cs, ci = torch.cat([best_s, ts], 1), torch.cat([best_i, ti + b0], 1)
+            best_s, pos = torch.topk(cs, k, dim=1)
+            best_i = torch.gather(ci, 1, pos)
+            del x, sc
+        return best_s.cpu().numpy(), best_i.cpu().numpy()
+
+    def case(name, rows_total, devices, nq, k, mask, mode, reps):
+        eng, lens_all = build(rows_total, devices, mask, mode != native.MODE_GEMV)
+        g = torch.Generator().manual_seed(4242)
+        q = torch.nn.functional.normalize(torch.randn((nq, 128), generator=g)).numpy()
+        kw = dict(qlen=np.full(nq, 150, np.int32), mincov=0.7) if mask else {}
+        for _ in range(5):
+            s, i = eng.search(q, k, mode=mode, **kw)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            s, i = eng.search(q, k, mode=mode, **kw)
+        dt = (time.perf_counter() - t0) / reps
+        sample = sorted(set([0, nq // 2, nq - 1]))
+        ws, wi = brute(rows_total, q[sample], k, mask, lens_all)
+        ok = bool(np.abs(s[sample] - ws).max() <= 1e-5 and ((i[sample] == wi) | (np.abs(s[sample] - ws) <= 1e-5)).all())
+        res["cases"].append({"case": name, "rows_total": rows_total, "shards": eng.n_shards, "devices": list(eng.devices), "nq": nq, "k": k,
+                             "path": "tc" if mode == native.MODE_TC else "gemv", "ms_per_call": dt * 1e3, "queries_per_s": nq / dt,
+                             "parity_checked": ok, "fallback_queries": eng.group.last_fallbacks()})
+        eng.close()
+        torch.cuda.empty_cache()
+
+    all_dev = list(range(ngpu))
+    case("cfg2 (CATH scale), engine's own choice", 500_000, None, 1, 10, True, native.MODE_GEMV, 2000)
+    if ngpu > 1:
+        case(f"cfg2 (CATH scale), forced over {ngpu} GPUs", 500_000, all_dev, 1, 10, True, native.MODE_GEMV, 2000)
+    per = 45_625_000
+    case(f"cfg4 (TED scale: 365M/8 rows per GPU x {ngpu}), 1 query", per * ngpu, all_dev, 1, 10, False, native.MODE_GEMV, 100)
+    case(f"cfg4 (TED scale: 365M/8 rows per GPU x {ngpu}), 1024-query batch", per * ngpu, all_dev, 1024, 10, False, native.MODE_TC, 10)
+    case("cfg3 (10M rows), 4096-query batch, engine's own choice", 10_000_000, None, 4096, 100, False, native.MODE_TC, 10)
+    res["api"] = "merizo_search_b200.engine.LocalEngine.search (fcs_group_search: host queries in, host scores/ids out, one host thread)"
+    return res
+
+
+# --------------------------------------------------------------------------------------------- parity (outside the timed region)
+PLANTED = 8  # queries replaced by database rows (spread over the whole id range, i.e. over every shard)
+
+
+def shard_blocks(r0, r1, rows_total, blk):
+    """The synthetic database is a GLOBAL matrix made of 2^20-row blocks (block b is generated from seed base+b, whoever
+    generates it); a shard [r0, r1) takes the slices of the blocks it overlaps.  Yields (block, rows in block, lo, hi):
+    rows [lo, hi) of the block are global rows [block*blk + lo, block*blk + hi)."""
+    b0 = r0
+    while b0 < r1:
+        gb = b0 // blk
+        lo, hi = b0 - gb * blk, min(r1, (gb + 1) * blk) - gb * blk
+        yield gb, min(blk, rows_total - gb * blk), lo, hi
+        b0 += hi - lo
+
+
+def planted_ids(rows_total):
+    return [int((2 * j + 1) * rows_total // (2 * PLANTED)) for j in range(PLANTED)]
+
+
+def plant_queries(q_dev, rows_total, dev, synth, blk, base_seed):
+    """Overwrite the first PLANTED queries with database rows (regenerated from their block seeds: every rank can do
+    this for any global id), so their top hit is known: the row itself, score 1."""
+    ids = planted_ids(rows_total)
+    for j, gid in enumerate(ids):
+        b = gid // blk
+        nb = min(blk, rows_total - b * blk)
+        x = synth.device_block(b, nb, dev, base_seed=base_seed)
+        q_dev[j] = x[gid - b * blk]
+        del x
+    return ids
+
+
+def parity_check(sc, ids, q_dev, k, wl, rows_total, r0, r1, lens_local, dev, synth, blk, base_seed, world, dist, torch):
+    """Result of one search (all queries, merged over ranks) against (1) the planted rows and (2) an independent
+    brute-force top-k (torch matmul + topk over this rank's regenerated shard, all-gathered and merged) on a sample of
+    the queries.  Same rule as the tests: scores within 1e-5, ids equal except inside score ties."""
+    out = {"planted_queries": PLANTED if (not wl["mask"] and q_dev.shape[0] >= PLANTED) else 0, "brute_force_queries": 0, "max_abs_score_diff": 0.0, "id_mismatches_beyond_ties": 0, "errors": []}
+    nq = q_dev.shape[0]
+    sc_h, ids_h = sc.cpu().numpy(), ids.cpu().numpy()
+    if not wl["mask"] and nq >= PLANTED:
+        for j, gid in enumerate(planted_ids(rows_total)):
+            if ids_h[j, 0] != gid or abs(float(sc_h[j, 0]) - 1.0) > 1e-5:
+                out["errors"].append(f"planted query {j}: expected row {gid} at rank 0 with score 1, got {int(ids_h[j, 0])} / {float(sc_h[j, 0]):.6f}")
+    if not ((np.diff(sc_h, axis=1) <= 0).all()):
+        out["errors"].append("scores not sorted")
+    sample = sorted(set(i for i in [0, 1, nq // 2, nq - 1] + ([PLANTED, 2 * PLANTED + 1] if nq > 2 * PLANTED + 1 else []) if 0 <= i < nq))
+    qs = q_dev[sample].clone()
+    best_s = torch.full((len(sample), k), -float("inf"), device=dev)
+    best_i = torch.full((len(sample), k), -1, dtype=torch.int64, device=dev)
+    for gb, nrows_b, lo, hi in shard_blocks(r0, r1, rows_total, blk):
+        x = synth.device_block(gb, nrows_b, dev, base_seed=base_seed)[lo:hi]
+        g0 = gb * blk + lo  # global id of x[0]
+        s = qs @ x.T
+        if wl["mask"]:  # (qlen >= lengths * mincov).float(), an fp32 product (reference dbsearch.py:76)
+            need = lens_local[g0 - r0:g0 - r0 + (hi - lo)].to(torch.float32) * torch.tensor(0.7, dtype=torch.float32, device=dev)
+            s = s * (torch.tensor(150.0, device=dev) >= need).to(torch.float32)[None, :]
+        ts, ti = torch.topk(s, min(k, hi - lo), dim=1)
+        cs, ci = torch.cat([best_s, ts], 1), torch.cat([best_i, ti + g0], 1)
+        best_s, pos = torch.topk(cs, k, dim=1)
+        best_i = torch.gather(ci, 1, pos)
+        del x, s
+    if world > 1:
+        gs = torch.empty((world,) + tuple(best_s.shape), device=dev)
+        gi = torch.empty((world,) + tuple(best_i.shape), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(gs.view(world * len(sample), k), best_s.contiguous())
+        dist.all_gather_into_tensor(gi.view(world * len(sample), k), best_i.contiguous())
+        cs = gs.permute(1, 0, 2).reshape(len(sample), world * k)
+        ci = gi.permute(1, 0, 2).reshape(len(sample), world * k)
+        # replicated layouts gather the same shard several times: drop duplicate ids before the final top-k
+        order = torch.argsort(ci, dim=1, stable=True)
+        ci, cs = torch.gather(ci, 1, order), torch.gather(cs, 1, order)
+        dup = torch.zeros_like(ci, dtype=torch.bool)
+        dup[:, 1:] = ci[:, 1:] == ci[:, :-1]
+        cs = torch.where(dup, torch.full_like(cs, -float("inf")), cs)
+        best_s, pos = torch.topk(cs, k, dim=1)
+        best_i = torch.gather(ci, 1, pos)
+    ws, wi = best_s.cpu().numpy(), best_i.cpu().numpy()
+    got_s, got_i = sc_h[sample], ids_h[sample]
+    out["brute_force_queries"] = len(sample)
+    diff = np.abs(got_s - ws)
+    out["max_abs_score_diff"] = float(diff.max())
+    if diff.max() > 1e-5:
+        out["errors"].append(f"score differs from brute force by {diff.max():.3e}")
+    mism = got_i != wi
+    if mism.any():
+        # an id mismatch is fine only inside a tie: the two rows' scores are within tolerance of each other
+        bad = int((mism & (diff > 1e-5)).sum())
+        tie_rows = mism.sum(axis=1)
+        if bad or (tie_rows > max(2, k // 10)).any():
+            out["id_mismatches_beyond_ties"] = int(mism.sum())
+            out["errors"].append(f"{int(mism.sum())} id mismatches against brute force")
+    out["ok"] = not out["errors"]
+    return out
+
+
 # --------------------------------------------------------------------------------------------- GPU arm
 def run_gpu(args, wl, wl_name, steps=None, warmup=None):
     """One workload on this rank's GPU; rank 0 returns the JSON dict (others None)."""
@@ -300,16 +586,7 @@ def run_gpu(args, wl, wl_name, steps=None, warmup=None):
     # N>1 layout: world = R row shards x Q query groups (engine.DistributedEngine); Q=1 is pure row sharding
     from merizo_search_b200.engine import DistributedEngine
 
-    qg = args.query_groups
-    if world == 1:
-        qg = 1
-    elif wl["scaling"] == "weak":
-        qg = 1  # the TED-scale slices are the row-sharded configuration of the metric: never replicate them
-    elif qg <= 0:
-        qg = DistributedEngine.auto_query_groups(rows_total, world, bytes_per_row=514 + (256 if wl["mode"] == "tc" else 0))
-    while qg > 1 and (world % qg != 0 or qg > nq):
-        qg -= 1
-    n_shards = world // qg
+    qg, n_shards = layout(wl, rows_total, world, args.query_groups)
     r0, r1 = shard_ranges(rows_total, n_shards)[rank // qg]
     n_local = r1 - r0
     nq_local = -(-nq // qg)
@@ -322,10 +599,10 @@ def run_gpu(args, wl, wl_name, steps=None, warmup=None):
     lens_all = None
     if wl["mask"]:
         lens_all = torch.from_numpy(synth.host_lengths(rows_total)[r0:r1].astype(np.int32)).to(dev)
-    for b0 in range(0, n_local, blk):
-        nb = min(blk, n_local - b0)
-        x = synth.device_block((r0 + b0) // blk, nb, dev, base_seed=1000)
-        h.upload_device(b0, nb, x.data_ptr(), lens_all[b0:b0 + nb].contiguous().data_ptr() if wl["mask"] else None)
+    for gb, nrows_b, lo, hi in shard_blocks(r0, r1, rows_total, blk):
+        x = synth.device_block(gb, nrows_b, dev, base_seed=1000)[lo:hi].contiguous()
+        b0 = gb * blk + lo - r0  # first local row of this slice
+        h.upload_device(b0, hi - lo, x.data_ptr(), lens_all[b0:b0 + hi - lo].contiguous().data_ptr() if wl["mask"] else None)
         del x
     h.finalize()
     torch.cuda.synchronize()
@@ -334,6 +611,8 @@ def run_gpu(args, wl, wl_name, steps=None, warmup=None):
     g = torch.Generator(device=dev)
     g.manual_seed(4242)  # same queries on every rank (replicated)
     q_dev = torch.nn.functional.normalize(torch.randn((nq, 128), device=dev, generator=g))
+    if not wl["mask"] and nq >= PLANTED:
+        plant_queries(q_dev, rows_total, dev, synth, blk, 1000)
     q_host = q_dev.cpu().pin_memory()
     qlen = np.full(nq, 150, np.int32) if wl["mask"] else None
     mincov = 0.7 if wl["mask"] else 0.0
@@ -371,6 +650,20 @@ def run_gpu(args, wl, wl_name, steps=None, warmup=None):
         step_device()
     barrier()
     launches_per_search = int(h.timing().last_launches)
+    # ---- parity, outside the timed region: the warm-up's last result against planted rows and a brute-force sample
+    with torch.cuda.stream(stream):
+        if world == 1:
+            chk_sc, chk_ids = sc, ids
+        else:
+            chk_sc, chk_ids = deng.search(q_dev, k, qlen=qlen, mincov=mincov, mode=mode)
+    barrier()
+    parity = parity_check(chk_sc, chk_ids, q_dev, k, wl, rows_total, r0, r1, lens_all, dev, synth, blk, 1000, world, dist, torch)
+    if world > 1:
+        okt = torch.tensor([1 if parity["ok"] else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(okt, op=dist.ReduceOp.MIN)  # every rank holds the merged result: all of them must agree
+        parity["ok_all_ranks"] = bool(int(okt.item()))
+        parity["ok"] = parity["ok"] and parity["ok_all_ranks"]
+    barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     launches = 0
     kernel_ms = []
@@ -385,12 +678,10 @@ def run_gpu(args, wl, wl_name, steps=None, warmup=None):
     ms_total = e0.elapsed_time(e1)
     clocks = sampler.stop() if sampler else None
     if wl["mode"] == "tc":
-        # dominant-kernel time: event pairs around every GEMM+filter launch inside the library, read back per search
-        # (reading them waits for the search, so this runs after the timed region, on a few extra searches)
-        for _ in range(min(args.steps, 5)):
-            step_device()
-            kernel_ms.append(h.timing().last_kernel_ms)
-        barrier()
+        # dominant-kernel time: event pairs around every GEMM+filter launch inside the library.  Read once, after the
+        # timed region, for its LAST search -- a search that ran under the sustained clocks of the loop (searches run
+        # one at a time with host round trips in between boost higher and would flatter the roofline)
+        kernel_ms.append(h.timing().last_kernel_ms)
     else:
         kernel_ms = [ms_total / args.steps]  # one kernel per step, launched back to back
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
@@ -431,31 +722,34 @@ def run_gpu(args, wl, wl_name, steps=None, warmup=None):
             flops = 2.0 * nq_local * n_local * 128  # this GPU's share: its query slice against its row shard
             achieved = flops / (kms * 1e-3) / 1e12
             roof = dict(bound="tensor", achieved=achieved, peak=peaks["tensor"], unit="TFLOP/s", frac=achieved / peaks["tensor"],
-                        traffic=None, kernel="tc_gemm_filter_kernel (all rounds of one search)",
-                        algorithmic="2*nq*rows*128 flop per search", peak_source=peaks["source"] + ", sustained bf16")
+                        traffic=None, kernel="tc_gemm_filter_kernel (all rounds of one search, timed inside the sustained loop)",
+                        algorithmic="2*nq*rows*128 flop per search", peak_source=peaks["source"] + ", sustained bf16 (the kernel is timed "
+                        "inside a long step)", peak_burst=peaks["tensor_burst"], frac_burst=achieved / peaks["tensor_burst"],
+                        step_frac=(flops / (ms_per_step * 1e-3) / 1e12) / peaks["tensor"])
         else:
             bpr = 512 + (2 if wl["mask"] else 0)
             byts = float(n_local) * bpr
             achieved = byts / (kms * 1e-3) / 1e9
             roof = dict(bound="hbm", achieved=achieved, peak=peaks["hbm"], unit="GB/s", frac=achieved / peaks["hbm"], traffic=None,
                         kernel="gemv_topk_kernel", algorithmic=f"{bpr} B per row per launch", peak_source=peaks["source"])
+        # dram bytes per launch come from an ncu --set full capture of exactly this workload on ONE GPU (profiles/); a rank
+        # of an N-GPU run does a different amount of work per launch, so no figure is quoted there
         prof = os.path.join(ROOT, "profiles", f"traffic_{wl_name}.json")
-        if os.path.exists(prof):
+        if world == 1 and not args.rows and not args.nq and os.path.exists(prof):
             with open(prof) as fh:
-                roof["traffic"] = json.load(fh).get("dram_bytes_per_launch")
+                tj = json.load(fh)
+            roof["traffic"] = tj.get("dram_bytes_per_launch")
+            roof["traffic_source"] = f"profiles/traffic_{wl_name}.json ({tj.get('captured', 'ncu --set full, one search')})"
         out = {
             "metric": "queries/s (exact top-k vs 128-d DB)", "value": value, "unit": "queries/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": wl["scaling"], "vs_baseline": None,
             "dtype": "bf16 tensor-core contraction + fp32 exact rescore" if wl["mode"] == "tc" else "f32",
             "data": "synthetic (i.i.d. N(0,1) rows, L2-normalised, generated on device per 2^20-row block; random unit queries)",
-            "config": {"workload": wl_name, "description": wl["desc"], "rows_total": rows_total, "rows_per_gpu": n_local,
-                       "nq": nq, "k": k, "path": wl["mode"], "coverage_mask": wl["mask"],
-                       "l2": "inputs larger than L2 (database streamed from HBM every step)",
-                       "parallelism": (f"{n_shards} row shard(s) x {qg} query group(s) over {world} ranks, one NCCL all-gather of "
-                                       "packed keys + GPU merge") if world > 1 else "single GPU",
-                       "queries_per_gpu": nq_local,
-                       "db_load_s": round(t_load, 2), "tc_fallback_queries": int(timing.last_tc_fallbacks)},
+            "config": make_config(wl, wl_name, rows_total, n_local, world, n_shards, qg, nq_local,
+                                  {"db_load_s": round(t_load, 2), "tc_fallback_queries": int(timing.last_tc_fallbacks),
+                                   "tc_rounds": int(timing.last_rounds)}),
+            "parity_checked": bool(parity["ok"]), "parity": parity,
             "e2e": {"value": nq / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": int(nq * 512),
                     "d2h_bytes_per_step": int(nq * k * 12), "ms_per_step": e2e_s * 1e3,
                     "api": ("merizo_search_b200.native.Database.search (fcs_search: pinned host queries in, host scores/ids out)"
@@ -479,7 +773,7 @@ def main():
     ap.add_argument("--steps", type=int, default=0)
     ap.add_argument("--warmup", type=int, default=0)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default=os.environ.get("FCS_BENCH_WORKLOAD", DEFAULT_WORKLOAD), choices=sorted(WORKLOADS) + ["embed"])
+    ap.add_argument("--workload", default=os.environ.get("FCS_BENCH_WORKLOAD", DEFAULT_WORKLOAD), choices=sorted(WORKLOADS) + ["embed", "local"])
     ap.add_argument("--rows", type=int, default=0, help="override the total row count (debugging)")
     ap.add_argument("--nq", type=int, default=0, help="override the batch size (debugging)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -488,6 +782,10 @@ def main():
                     help="N>1: ranks = row shards x query groups; 0 = auto (replicate the database as far as ~80 GB per "
                          "GPU allow and split the batch), 1 = pure row sharding")
     args = ap.parse_args()
+    if args.workload == "local":  # single-process engine over all visible GPUs (not under torchrun)
+        if int(os.environ.get("RANK", "0")) == 0:
+            print(json.dumps({"workload": "local", **run_local(args)}))
+        return 0
     if args.workload == "embed":  # the step before the search, alone (1 GPU)
         if int(os.environ.get("RANK", "0")) != 0:
             return 0
@@ -520,6 +818,7 @@ def main():
         if rank != 0:
             return 0
         rows_total = args.rows or wl["rows"] * (world if wl["scaling"] == "weak" else 1)
+        ref_qg, ref_shards = layout(wl, rows_total, world, args.query_groups)
         vals = []
         cores = sample = None
         for _ in range(max(1, min(args.steps, 3))):
@@ -530,7 +829,9 @@ def main():
             "impl": "reference", "metric": "queries/s (exact top-k vs 128-d DB)", "value": v, "unit": "queries/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wl["nq"] / v,
             "higher_is_better": True, "scaling": wl["scaling"], "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "description": wl["desc"], "rows_total": rows_total, "nq": wl["nq"], "k": wl["k"]},
+            # same keys and values as the GPU arm's config (the layout fields describe the GPU arm this line is compared with)
+            "config": make_config(wl, args.workload, rows_total, -(-rows_total // ref_shards), world, ref_shards, ref_qg,
+                                  -(-wl["nq"] // ref_qg), {"db_load_s": None, "tc_fallback_queries": 0, "tc_rounds": 0}),
             "cpu_baseline": {"value": v, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }))
@@ -542,18 +843,25 @@ def main():
     # slice (the full database at N=8); cfg2 is the CATH-scale single-query case (1 GPU only).
     extra = {}
     if not args.no_extra:
-        # cfg5 (65,536 queries, k=50) is run explicitly (--workload cfg5): its 1-GPU slice is in profiles/, the 8-GPU run has
-        # not been validated yet and an extra must never be able to stall the primary line
-        others = [w for w in (("cfg4", "cfg4b", "cfg2") if world == 1 else ("cfg4", "cfg4b")) if w != args.workload]
+        # cfg5 (65,536 queries, k=50: BASELINE configs[4]) rides along at N=8, where the slices add up to the full 365 M-row
+        # TED-scale database; on fewer GPUs it runs with --workload cfg5 (1-GPU slice: profiles/)
+        others = [w for w in (("cfg4", "cfg4b", "cfg2") if world == 1 else (("cfg4", "cfg4b", "cfg5") if world == 8 else ("cfg4", "cfg4b")))
+                  if w != args.workload]
         for w in others:
             try:
                 o, _ = run_gpu(args, WORKLOADS[w], w, steps={"cfg4": 40, "cfg4b": 8, "cfg2": 2000, "cfg3": 10, "cfg5": 3}[w],
                                warmup=3 if w == "cfg5" else 5)
                 if rank == 0:
-                    extra[w] = {key: o[key] for key in ("value", "unit", "ms_per_step", "scaling", "e2e", "roofline", "config", "gpu_launches")}
+                    extra[w] = {key: o[key] for key in ("value", "unit", "ms_per_step", "scaling", "e2e", "roofline", "config", "gpu_launches",
+                                                        "parity_checked", "parity")}
             except Exception as exc:  # an extra must never take the primary line down
                 if rank == 0:
                     extra[w] = {"error": str(exc)[:300]}
+        if world == 1 and not args.nq:
+            try:
+                extra["loader"] = run_loader(args)
+            except Exception as exc:
+                extra["loader"] = {"error": str(exc)[:300]}
         if world == 1 and not args.nq:
             try:
                 o = run_embed(args, steps=3, warmup=3, cpu_baseline=not args.no_cpu_baseline)

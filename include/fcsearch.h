@@ -164,10 +164,10 @@ int fcs_get_timing(const fcs_db* db, fcs_timing* out);
 /* Test hook (not part of the drop-in surface): the approximate bf16 tensor-core score of every
  * (query,row) pair, out_scores [nq, n_rows] HOST fp32; only for shards of <= 4096 rows. */
 int fcs_debug_tc_approx(fcs_db* db, const float* q, int nq, int qnorm, float* out_scores);
-/* Test hooks: the round plan of the tensor-core path for a shard of n_rows rows (7 int64 per round: tiles, first sample
+/* Test hooks: the round plan of the tensor-core path for a shard of n_rows rows and a batch of nq queries (7 int64 per round: tiles, first sample
  * index, sample stride, complement size, round-0 flag, selection rank, partition flag; returns the number of rounds) and
  * the database tile a round visits at position idx. */
-int fcs_debug_tc_plan(int64_t n_rows, int kprime, int64_t* out_rounds, int max_rounds);
+int fcs_debug_tc_plan(int64_t n_rows, int kprime, int nq, int64_t* out_rounds, int max_rounds);
 int64_t fcs_debug_tc_tile_of(int64_t j0, int64_t stride, int64_t comp_t, int64_t idx);
 
 #ifdef __cplusplus

@@ -27,7 +27,14 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC",
     "-Xcompiler", "-pthread",
     "-cudart", "static",
-] + (["-DFCS_TC_TRACE"] if os.environ.get("FCS_TC_TRACE") else [])
+] + (["-DFCS_TC_TRACE"] if os.environ.get("FCS_TC_TRACE") else []) + \
+    ([f"-DFCS_TC_SLOWPATH={int(os.environ['FCS_TC_SLOWPATH'])}"] if os.environ.get("FCS_TC_SLOWPATH") else []) + \
+    [f"-D{k}={int(v)}" for k, v in sorted(os.environ.items()) if k.startswith("FCS_TC_") and k in ("FCS_TC_BPOLICY", "FCS_TC_RASTER")]
+# experiments: FCS_LIB_VARIANT=name builds/loads libfcsearch_<name>.so next to the default library
+_VARIANT = os.environ.get("FCS_LIB_VARIANT", "")
+if _VARIANT:
+    LIB_PATH = os.path.join(PKG_DIR, f"libfcsearch_{_VARIANT}.so")
+    STAMP_PATH = os.path.join(PKG_DIR, f".libfcsearch_{_VARIANT}.stamp")
 
 
 def _nvcc() -> str:
@@ -76,7 +83,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 def _build_locked(verbose: bool) -> str:
     nvcc = _nvcc()
     objs = []
-    build_dir = os.path.join(PKG_DIR, "build")
+    build_dir = os.path.join(PKG_DIR, "build" + ("_" + _VARIANT if _VARIANT else ""))
     os.makedirs(build_dir, exist_ok=True)
     procs = []
     for src in SOURCES:

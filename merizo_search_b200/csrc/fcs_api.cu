@@ -59,7 +59,7 @@ void parallel_memcpy(void* dst, const void* src, size_t bytes) {
 // the number of readers); returns 0 or an errno
 int parallel_pread(int fd, void* dst, size_t bytes, int64_t offset) {
     unsigned hw = std::thread::hardware_concurrency();
-    const size_t nthreads = bytes < (size_t(4) << 20) ? 1 : (hw >= 8 ? 4 : (hw >= 4 ? 2 : 1));
+    const size_t nthreads = bytes < (size_t(4) << 20) ? 1 : (hw >= 16 ? 8 : (hw >= 8 ? 4 : (hw >= 4 ? 2 : 1)));
     const size_t per = ((bytes / nthreads) + 4095) & ~size_t(4095);
     std::vector<int> err(nthreads, 0);
     auto body = [&](size_t t) {
@@ -541,7 +541,9 @@ int fcs::api_search_core(fcs_db* db, const float* q_dev, int nq, const int32_t* 
         pd.out_ids = out_ids;
         pd.out_keys = out_keys;
         const int max_passes = (nq + GEMV_MAX_NQ - 1) / GEMV_MAX_NQ;
+        tc_phase_mark(db->tc, "exact-scan queue", stream);
         rc = fallback_passes(db, pd, 0, max_passes < FB_ASYNC_PASSES ? max_passes : FB_ASYNC_PASSES, stream, &launches);
+        tc_phase_mark(db->tc, "end", stream);
         db->pending = pd;
     }
     if (rc != FCS_OK) return rc;
@@ -631,9 +633,9 @@ extern "C" int fcs_debug_tc_approx(fcs_db* db, const float* q, int nq, int qnorm
     return FCS_OK;
 }
 
-extern "C" int fcs_debug_tc_plan(int64_t n_rows, int kprime, int64_t* out_rounds, int max_rounds) {
-    if (n_rows < 1 || !out_rounds || max_rounds < 1) return FCS_FAIL(FCS_ERR_INVALID, "fcs_debug_tc_plan: bad argument");
-    return tc_debug_plan(n_rows, kprime > 0 ? kprime : tc_default_kprime(10), out_rounds, max_rounds);
+extern "C" int fcs_debug_tc_plan(int64_t n_rows, int kprime, int nq, int64_t* out_rounds, int max_rounds) {
+    if (n_rows < 1 || nq < 1 || !out_rounds || max_rounds < 1) return FCS_FAIL(FCS_ERR_INVALID, "fcs_debug_tc_plan: bad argument");
+    return tc_debug_plan(n_rows, kprime > 0 ? kprime : tc_default_kprime(10), (nq + 511) / 512, out_rounds, max_rounds);
 }
 
 extern "C" int64_t fcs_debug_tc_tile_of(int64_t j0, int64_t stride, int64_t comp_t, int64_t idx) {

@@ -32,7 +32,7 @@
 //   each followed by tc_select_kernel (one block per query, radix select on the order-preserving score word).
 //   Every tile is multiplied exactly once.  cfg3 (10 M rows) takes 3 GEMM launches instead of 9.
 //
-//   K4  tc_rescore_kernel -- one warp per query.  Phase A: the k' best approximate candidates are gathered
+//   K4  tc_rescore_kernel -- one block (4 warps) per query.  Phase A: the k' best approximate candidates are gathered
 //        (fp32 rows), their inner products recomputed exactly, the k best kept; certificate
 //        s_k(exact) > t' + eps with t' = the k'-th approximate score (every non-candidate has an approximate
 //        score <= t').  Phase B, only when A fails: ALL rows above the sweep threshold (they are still in the
@@ -52,6 +52,17 @@
 #include "fcs_common.cuh"
 #include "fcs_internal.h"
 #include "fcs_tc.h"
+
+#ifndef FCS_TC_SLOWPATH
+#define FCS_TC_SLOWPATH 1  // 1: a hit's 8-column group is re-read from TMEM (default); 0: hits are taken from the registers of
+                           // the 32-column load -- measured 7-10 % SLOWER on every workload (profiles/r02_experiments.md): keeping
+                           // the 32 registers live past the threshold test keeps the next tcgen05.ld from being issued early
+#endif
+
+#ifndef FCS_TC_BPOLICY
+#define FCS_TC_BPOLICY 1  // L2 policy of the DB tile copies: 1 evict_normal (default: the CTAs that sweep the same tiles for other
+                         // query groups find them in L2; cfg4b 8.97 vs 9.22 ms), 0 evict_first
+#endif
 
 namespace fcs {
 
@@ -281,13 +292,13 @@ __device__ long long g_trace[5][256];
 // y == ~0u: nothing reserved yet).  Deliberately NOT inlined: there are 32 call sites per 32-column part, and the
 // epilogue loop has to stay small enough for the instruction cache (an inlined append per column cost 3-5 k cycles
 // per hit in instruction-cache misses).
-__device__ __noinline__ uint2 tc_append(unsigned* cnt_q, uint64_t* cand_q, uint2 res, int res_block, uint64_t key) {
+__device__ __noinline__ uint2 tc_append(unsigned* cnt_q, uint64_t* cand_q, uint2 res, int res_block, uint32_t score_bits, uint32_t row) {
     if (res.y >= unsigned(res_block)) {
         res.x = atomicAdd(cnt_q, unsigned(res_block));
         res.y = 0;
     }
     const unsigned slot = res.x + res.y++;
-    if (slot < unsigned(TC_CAP)) cand_q[slot] = key;
+    if (slot < unsigned(TC_CAP)) cand_q[slot] = make_key(__uint_as_float(score_bits), row);
     return res;
 }
 // unused slots of the last reservation must read as empty
@@ -345,7 +356,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_filter_kernel(const TcG
     if (warp == 0) {
         // ---------------------------------------------------------------- TMA producer
         if (lane == 0) {
+#if FCS_TC_BPOLICY == 0
             const uint64_t pol_stream = policy_evict_first();
+#else
+            const uint64_t pol_stream = policy_evict_normal();
+#endif
             const uint64_t pol_keep = policy_evict_normal();
             uint32_t it = 0, seg = 0;
             for (int64_t s = s_begin; s < s_end; ++seg) {
@@ -455,45 +470,37 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_filter_kernel(const TcG
                     if (lane == 0) mbar_arrive(&tmem_empty[t]);
                     continue;
                 }
-                // Two hits per tile are parked in registers and appended after the accumulator has been handed back to
-                // the MMA issuer (the append's atomic and store are off the critical path); further hits are appended
-                // at once.  A parked hit is (score bits, column of the tile).
-                int pend_n = 0;
-                uint32_t pend_v0 = 0, pend_v1 = 0;
-                int pend_c0 = 0, pend_c1 = 0;
-                // Fast path: 32 scores per tcgen05.ld, reduced with 3-input max, one compare against the threshold.
-                // Slow path (some lane of the warp has a hit among these 32 columns): the scores are still in
-                // registers; 32 predicated column checks, no second TMEM read.
+                // rows of this tile that exist (the last tile of the shard is zero-padded)
+                const int64_t left = p.n_rows - row_base;
+                const int rows_here = left < TC_N ? int(left) : TC_N;
+                // Fast path: 32 scores per tcgen05.ld, reduced with 3-input max to one maximum per 8 columns, one compare
+                // against the threshold.  Slow path (some lane of the warp has a hit among these 32 columns): the scores
+                // are still in registers -- no second TMEM read; the 8-column maxima gate the column checks, so a hit costs
+                // ~50 issue slots of the warp.  That count is what matters: the 16 epilogue warps share the schedulers
+                // with the MMA issuers, and an epilogue that issues more than ~2 k instructions per tile step slows the
+                // GEMM itself (a version with 32 unconditional column checks per hit part ran the sweep 27 % slower).
+#if FCS_TC_SLOWPATH == 0
 #pragma unroll 1
                 for (int part = 0; part < TC_N / 32; ++part) {
                     uint32_t r[32];
                     tc_ld32(tmem_base + lane_base + uint32_t(t * TC_N + part * 32), r);
                     tc_wait_ld();
                     const float* f = reinterpret_cast<const float*>(r);
-                    float mx;
-                    {
-                        float m[4];
+                    float m[4];
 #pragma unroll
-                        for (int g = 0; g < 4; ++g)
-                            m[g] = fmaxf(max3(f[g * 8], f[g * 8 + 1], f[g * 8 + 2]), max3(max3(f[g * 8 + 3], f[g * 8 + 4], f[g * 8 + 5]), f[g * 8 + 6], f[g * 8 + 7]));
-                        mx = fmaxf(max3(m[0], m[1], m[2]), m[3]);
-                    }
+                    for (int g = 0; g < 4; ++g)
+                        m[g] = fmaxf(max3(f[g * 8], f[g * 8 + 1], f[g * 8 + 2]), max3(max3(f[g * 8 + 3], f[g * 8 + 4], f[g * 8 + 5]), f[g * 8 + 6], f[g * 8 + 7]));
+                    const float mx = fmaxf(max3(m[0], m[1], m[2]), m[3]);
                     if (__any_sync(FULL, mx > thr)) {  // rare once the threshold is warm
                         if (mx > thr) {
 #pragma unroll
-                            for (int c = 0; c < 32; ++c) {
-                                if (f[c] > thr) {
-                                    const int col = part * 32 + c;
-                                    if (pend_n == 0) {
-                                        pend_v0 = r[c];
-                                        pend_c0 = col;
-                                        pend_n = 1;
-                                    } else if (pend_n == 1) {
-                                        pend_v1 = r[c];
-                                        pend_c1 = col;
-                                        pend_n = 2;
-                                    } else if (row_base + col < p.n_rows) {
-                                        res = tc_append(cnt_q, cand_q, res, p.res_block, make_key(f[c], uint32_t(row_base + col)));
+                            for (int g = 0; g < 4; ++g) {
+                                if (m[g] > thr) {
+#pragma unroll
+                                    for (int c = 0; c < 8; ++c) {
+                                        const int col = part * 32 + g * 8 + c;
+                                        if (f[g * 8 + c] > thr && col < rows_here)
+                                            res = tc_append(cnt_q, cand_q, res, p.res_block, r[g * 8 + c], uint32_t(row_base) + uint32_t(col));
                                     }
                                 }
                             }
@@ -501,14 +508,53 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_filter_kernel(const TcG
                         __syncwarp();
                     }
                 }
+#else
+#pragma unroll 1
+                for (int part = 0; part < TC_N / 32; ++part) {
+                    const uint32_t taddr = tmem_base + lane_base + uint32_t(t * TC_N + part * 32);
+                    float m[4];
+                    {
+                        uint32_t r[32];
+                        tc_ld32(taddr, r);
+                        tc_wait_ld();
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            const float* f = reinterpret_cast<const float*>(&r[g * 8]);
+                            m[g] = fmaxf(max3(f[0], f[1], f[2]), max3(max3(f[3], f[4], f[5]), f[6], f[7]));
+                        }
+                    }
+                    const float mx = fmaxf(max3(m[0], m[1], m[2]), m[3]);
+                    if (__any_sync(FULL, mx > thr)) {  // rare once the threshold is warm
+                        unsigned wgm = 0;  // groups in which some lane has a hit (warp-uniform)
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) wgm |= __any_sync(FULL, m[g] > thr) ? (1u << g) : 0u;
+                        while (wgm) {
+                            const int g = __ffs(wgm) - 1;
+                            wgm &= wgm - 1;
+                            uint32_t v8[8];
+                            __syncwarp();  // lanes left the divergent append loop below at different times
+                            tc_ld8(taddr + uint32_t(g * 8), v8);
+                            tc_wait_ld();
+                            unsigned hits = 0;
+#pragma unroll
+                            for (int c = 0; c < 8; ++c) hits |= (__uint_as_float(v8[c]) > thr) ? (1u << c) : 0u;
+                            while (hits) {
+                                const int c = __ffs(hits) - 1;
+                                hits &= hits - 1;
+                                uint32_t bits = v8[0];
+#pragma unroll
+                                for (int cc = 1; cc < 8; ++cc) bits = (c == cc) ? v8[cc] : bits;
+                                const int col = part * 32 + g * 8 + c;
+                                if (col < rows_here) res = tc_append(cnt_q, cand_q, res, p.res_block, bits, uint32_t(row_base) + uint32_t(col));
+                            }
+                        }
+                    }
+                }
+#endif
                 TRACE(3, it, blockIdx.x == 0 && warp == 5 && lane == 0);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tmem_empty[t]);
-                if (pend_n > 0 && row_base + pend_c0 < p.n_rows)
-                    res = tc_append(cnt_q, cand_q, res, p.res_block, make_key(__uint_as_float(pend_v0), uint32_t(row_base + pend_c0)));
-                if (pend_n > 1 && row_base + pend_c1 < p.n_rows)
-                    res = tc_append(cnt_q, cand_q, res, p.res_block, make_key(__uint_as_float(pend_v1), uint32_t(row_base + pend_c1)));
                 TRACE(4, it, blockIdx.x == 0 && warp == 5 && lane == 0);
             }
             if (!p.first_round) tc_close_reservation(cand_q, res, p.res_block);
@@ -734,10 +780,35 @@ __device__ __forceinline__ void rescore_range(const TcRescoreParams& p, const ui
     }
 }
 
+// the WPQ warps of a query hold one sorted list each: its first warp ends up with the k best of the union
+template <int WPQ>
+__device__ __forceinline__ void rescore_merge_block(WarpTopK<4>& tk, uint64_t (*s_lists)[128], int warp, int lane, int k) {
+    if (WPQ == 1) return;
+    if (warp > 0) tk.store(s_lists[warp - 1], lane, 128);
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll 1
+        for (int w = 0; w < WPQ - 1; ++w) {
+            WarpTopK<4> other;
+            other.template load<false>(s_lists[w], lane, 128);
+            tk.merge_sorted(other.key, lane, k);
+        }
+    }
+    __syncthreads();
+}
+
+// WPQ = 4: one block (4 warps) per query -- small batches, where the chain of dependent gathers of one query sets the
+// kernel's duration (512 queries: 53 us instead of 114 us); WPQ = 1: one warp per query, four queries per block -- large
+// batches, where the extra merges and barriers cost more than the parallelism buys (4096 queries: 137 us vs 209 us).
+template <int WPQ>
 __global__ void __launch_bounds__(128) tc_rescore_kernel(const TcRescoreParams p) {
+    __shared__ uint64_t s_lists[WPQ > 1 ? WPQ - 1 : 1][128];
+    __shared__ int s_phase_b_all[4];
     const int lane = threadIdx.x & 31;
-    const int q = blockIdx.x * 4 + (threadIdx.x >> 5);
-    if (q >= p.nq) return;
+    const int warp = WPQ == 1 ? 0 : int(threadIdx.x >> 5);   // warp index within the query's team
+    const int q = WPQ == 1 ? int(blockIdx.x) * 4 + int(threadIdx.x >> 5) : int(blockIdx.x);
+    if (q >= p.nq) return;  // WPQ == 1 only: whole warps leave, no block barrier follows for them
+    int& s_phase_b = s_phase_b_all[WPQ == 1 ? (threadIdx.x >> 5) : 0];
     const int n_all = int(p.cnt[q]);
     const int n_sel = int(p.sel_cnt[q]);
     const unsigned fl = p.flags[q];
@@ -749,18 +820,37 @@ __global__ void __launch_bounds__(128) tc_rescore_kernel(const TcRescoreParams p
     // Phase A.  Every row that is NOT among the k' selected candidates has an approximate score <= t' and therefore an
     // exact score <= t' + eps: the k best of the candidates are the k best of the shard if the k-th exact score beats that.
     // t' = -inf means every row of the shard is a candidate (shards of at most 4096 rows with fewer than k' rows).
-    rescore_range(p, cand, q4, 0, n_sel, tk, lane);
+    {
+        const int per = ((n_sel + WPQ - 1) / WPQ + 31) & ~31;
+        const int lo = warp * per < n_sel ? warp * per : n_sel;
+        const int hi = lo + per < n_sel ? lo + per : n_sel;
+        rescore_range(p, cand, q4, lo, hi, tk, lane);
+    }
+    rescore_merge_block<WPQ>(tk, s_lists, warp, lane, p.k);
     bool ok = false;
-    if (!(fl & 1u)) {
-        const float tprime = p.thr_sel[q];
-        ok = (tprime == -INFINITY) || (key_score(tk.thr) > tprime + eps);
-        if (!ok && n_all > n_sel) {
-            // Phase B: all the rows above the last round's threshold are in the buffer; rescore the rest of them too.
-            rescore_range(p, cand, q4, n_sel, n_all, tk, lane);
+    if (warp == 0) {
+        if (!(fl & 1u)) {
+            const float tprime = p.thr_sel[q];
+            ok = (tprime == -INFINITY) || (key_score(tk.thr) > tprime + eps);
+        }
+        if (lane == 0) s_phase_b = (!ok && !(fl & 1u) && n_all > n_sel) ? 1 : 0;
+    }
+    if (WPQ == 1) __syncwarp(); else __syncthreads();
+    if (s_phase_b) {
+        // Phase B: all the rows above the last round's threshold are in the buffer; rescore the rest of them too.
+        if (warp > 0) tk.init();
+        const int n_rest = n_all - n_sel;
+        const int per = ((n_rest + WPQ - 1) / WPQ + 31) & ~31;
+        const int lo = n_sel + (warp * per < n_rest ? warp * per : n_rest);
+        const int hi = lo + per < n_all ? lo + per : n_all;
+        rescore_range(p, cand, q4, lo, hi, tk, lane);
+        rescore_merge_block<WPQ>(tk, s_lists, warp, lane, p.k);
+        if (warp == 0) {
             const float tround = p.thr[q];
             ok = (tround == -INFINITY) || (key_score(tk.thr) > tround + eps);
         }
     }
+    if (warp != 0) return;
     if (!ok) {  // queue the query for the exact scan (device-side: the scan kernels read the queue length themselves)
         unsigned slot = 0;
         if (lane == 0) {
@@ -839,7 +929,7 @@ struct TcState {
     unsigned* n_flagged = nullptr;    // device: [0] fallback queue length, [1..2] build statistics
     unsigned* h_n_flagged = nullptr;  // pinned copy of [0], refreshed at the end of every search
     // plan parameters (FCS_TC_* environment overrides, for sweeps)
-    double cf_mult = 3.0, cf_min = 512.0, m_final = 24.0, c_sample = 128.0, m_min = 16.0;
+    double cf_mult = 2.4, cf_min = 384.0, m_final = 24.0, c_sample = 128.0, m_min = 16.0;
     bool verbose = false;
     // timing of the dominant kernel: one event pair per K3 launch of the last search
     static constexpr int MAX_ROUNDS = 16;
@@ -850,6 +940,7 @@ struct TcState {
     // FCS_TC_PHASES=1: an event in front of every kernel of a search, printed by tc_last_kernel_ms (diagnostics)
     bool phases = false;
     int r0_tiles = TC_R0_TILES;
+    bool r0_auto = true;
     std::vector<cudaEvent_t> pev;
     std::vector<std::string> plabel;
     int n_pev = 0;
@@ -867,14 +958,17 @@ static void tc_phase(TcState* s, const char* label, cudaStream_t stream) {
     cudaEventRecord(s->pev[s->n_pev++], stream);
 }
 
-static std::vector<TcRound> tc_plan(const TcState* s, int kp) {
+static std::vector<TcRound> tc_plan(const TcState* s, int kp, int n_qgroups) {
     std::vector<TcRound> plan;
     const int64_t nt = s->n_tiles;
     if (nt <= TC_R0_TILES) {  // the whole shard fits the candidate buffer: one round records everything
         plan.push_back({nt, 0, 1, 0, 1, kp, 1});
         return plan;
     }
-    const int64_t t0 = nt / 2 < s->r0_tiles ? nt / 2 : s->r0_tiles;
+    // round 0 records every score: keep it to one wave of CTAs (query groups x tiles <= SMs) for large batches
+    int r0 = s->r0_tiles;
+    if (s->r0_auto) r0 = n_qgroups <= 4 ? 32 : (n_qgroups <= 9 ? 16 : 8);
+    const int64_t t0 = nt / 2 < r0 ? nt / 2 : r0;
     const double cf = std::fmax(s->cf_mult * kp, s->cf_min);  // rows expected above the sweep threshold
     int64_t t_last = int64_t(std::ceil(double(nt) * s->m_final / cf));
     if (t_last > nt / 2) t_last = nt / 2;
@@ -916,6 +1010,10 @@ static std::vector<TcRound> tc_plan(const TcState* s, int kp) {
     return plan;
 }
 
+void tc_phase_mark(TcState* s, const char* label, cudaStream_t stream) {
+    if (s) tc_phase(s, label, stream);
+}
+
 const char* tc_last_error() { return g_tc_error.c_str(); }
 int tc_min_batch() { return 32; }
 int tc_max_k() { return 128; }
@@ -930,7 +1028,7 @@ float tc_last_kernel_ms(TcState* s) {
         for (int i = 0; i + 1 < s->n_pev; ++i) {
             float ms = 0.f;
             cudaEventElapsedTime(&ms, s->pev[i], s->pev[i + 1]);
-            fprintf(stderr, "[fcs_tc] phase %-10s %8.1f us\n", s->plabel[i].c_str(), ms * 1e3f);
+            fprintf(stderr, "[fcs_tc] phase %-18s %8.1f us\n", s->plabel[i].c_str(), ms * 1e3f);
         }
     }
     for (int r = 0; r < s->last_rounds && r < TcState::MAX_ROUNDS; ++r) {
@@ -985,6 +1083,7 @@ int tc_create(TcState** out, int device, int sm_count, const float* rows, int64_
     s->c_sample = env_double("FCS_TC_C_SAMPLE", s->c_sample, 64.0, 2048.0);
     s->m_min = env_double("FCS_TC_M_MIN", s->m_min, 1.0, 64.0);
     s->r0_tiles = int(env_double("FCS_TC_R0_TILES", TC_R0_TILES, 1.0, TC_R0_TILES));
+    s->r0_auto = getenv("FCS_TC_R0_TILES") == nullptr;
     s->phases = getenv("FCS_TC_PHASES") != nullptr;
     auto run = [&]() -> int {
         TC_CUDA(cudaFuncSetAttribute(tc_gemm_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
@@ -992,7 +1091,8 @@ int tc_create(TcState** out, int device, int sm_count, const float* rows, int64_
         // so the SMs are not reconfigured (drained) twice per round
         TC_CUDA(cudaFuncSetAttribute(tc_select_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         TC_CUDA(cudaFuncSetAttribute(tc_prep_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        TC_CUDA(cudaFuncSetAttribute(tc_rescore_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        TC_CUDA(cudaFuncSetAttribute(tc_rescore_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        TC_CUDA(cudaFuncSetAttribute(tc_rescore_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         for (cudaEvent_t& e : s->ev) TC_CUDA(cudaEventCreate(&e));
         TC_CUDA(cudaEventCreateWithFlags(&s->ev_done, cudaEventDisableTiming));
         TC_CUDA(cudaMalloc(&s->b_img, size_t(s->n_tiles) * B_TILE_BYTES));
@@ -1089,9 +1189,13 @@ int tc_search(TcState* s, const float* q_dev, int nq, int k, int kprime, int qno
     if (rc != FCS_OK) return rc;
     const int n_qgroups = (nq + TC_QGROUP - 1) / TC_QGROUP;
     const int nq_pad = n_qgroups * TC_QGROUP;
-    const std::vector<TcRound> plan = tc_plan(s, kp);
+    const std::vector<TcRound> plan = tc_plan(s, kp, n_qgroups);
 
-    s->n_pev = 0;
+    if (s->phases && s->n_pev > 0) {  // keep the previous search's last event: the gap between two searches is a phase too
+        std::swap(s->pev[0], s->pev[s->n_pev - 1]);
+        s->plabel[0] = "(between searches)";
+        s->n_pev = 1;
+    }
     tc_phase(s, "prep", stream);
     tc_launch_prep(s, q_dev, nq, nq_pad, qnorm, unsigned(plan[0].n_idx * TC_N), stream);
     TC_CUDA(cudaGetLastError());
@@ -1124,12 +1228,12 @@ int tc_search(TcState* s, const float* q_dev, int nq, int k, int kprime, int qno
     rp.fb_list = s->fb_list; rp.fb_q = s->fb_q; rp.nq = nq; rp.k = k; rp.id_base = s->id_base;
     rp.out_keys = out_keys; rp.out_scores = out_scores; rp.out_ids = out_ids;
     tc_phase(s, "rescore", stream);
-    tc_rescore_kernel<<<(nq + 3) / 4, 128, 0, stream>>>(rp);
+    if (nq <= 2048) tc_rescore_kernel<4><<<nq, 128, 0, stream>>>(rp);
+    else tc_rescore_kernel<1><<<(nq + 3) / 4, 128, 0, stream>>>(rp);
     TC_CUDA(cudaGetLastError());
     ++*launches;
     tc_phase(s, "tail", stream);
     TC_CUDA(cudaMemcpyAsync(s->h_n_flagged, s->n_flagged, sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
-    tc_phase(s, "end", stream);
     TC_CUDA(cudaEventRecord(s->ev_done, stream));
     s->last_rounds = rounds;
     s->last_valid = true;
@@ -1152,11 +1256,11 @@ int tc_search(TcState* s, const float* q_dev, int nq, int k, int kprime, int qno
 }
 
 // Test hook: the round plan for a shard of n_rows rows and a given k' (what tc_search would launch).
-int tc_debug_plan(int64_t n_rows, int kprime, int64_t* out, int max_rounds) {
+int tc_debug_plan(int64_t n_rows, int kprime, int n_qgroups, int64_t* out, int max_rounds) {
     TcState s;
     s.n_rows = n_rows;
     s.n_tiles = (n_rows + TC_N - 1) / TC_N;
-    const std::vector<TcRound> plan = tc_plan(&s, kprime);
+    const std::vector<TcRound> plan = tc_plan(&s, kprime, n_qgroups);
     int n = 0;
     for (const TcRound& r : plan) {
         if (n >= max_rounds) break;

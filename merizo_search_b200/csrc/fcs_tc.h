@@ -30,8 +30,9 @@ int tc_search(TcState* s, const float* q_dev, int nq, int k, int kprime, int qno
               uint64_t* out_keys, cudaStream_t stream, int* launches, TcFallbackQueue* fbq);
 int tc_default_kprime(int k);
 int tc_debug_approx(TcState* s, const float* q_dev, int nq, int qnorm, float* out_host, cudaStream_t stream);
-int tc_debug_plan(int64_t n_rows, int kprime, int64_t* out, int max_rounds);
+int tc_debug_plan(int64_t n_rows, int kprime, int n_qgroups, int64_t* out, int max_rounds);
 int64_t tc_debug_tile_of(int64_t j0, int64_t stride, int64_t comp_T, int64_t idx);
+void tc_phase_mark(TcState* s, const char* label, cudaStream_t stream);  // diagnostics (FCS_TC_PHASES=1)
 const char* tc_last_error();
 int tc_min_batch();  // AUTO mode switches to the TC path at this many queries
 int tc_max_k();

@@ -107,7 +107,7 @@ def load() -> C.CDLL:
     lib.fcs_search.argtypes = [vp, vp, i32, vp, f32, i32, i32, i32, i32, vp, vp]
     lib.fcs_search_device.argtypes = [vp, vp, i32, vp, f32, i32, i32, i32, i32, vp, vp, vp, vp]
     lib.fcs_search_finish.argtypes = [vp, vp, C.POINTER(C.c_int)]
-    lib.fcs_debug_tc_plan.argtypes = [i64, i32, vp, i32]
+    lib.fcs_debug_tc_plan.argtypes = [i64, i32, i32, vp, i32]
     lib.fcs_debug_tc_tile_of.argtypes = [i64, i64, i64, i64]
     lib.fcs_merge_topk.argtypes = [i32, vp, i32, i32, i32, vp, vp, vp]
     lib.fcs_get_timing.argtypes = [vp, C.POINTER(Timing)]
@@ -327,10 +327,10 @@ ASYNC_FALLBACK_QUERIES = 32
 TC_PLAN_FIELDS = ("tiles", "j0", "stride", "comp_t", "first", "rank", "partition")
 
 
-def debug_tc_plan(n_rows: int, kprime: int = 0, max_rounds: int = 16):
-    """Test hook: the rounds the tensor-core path runs for a shard of n_rows rows (list of dicts, TC_PLAN_FIELDS)."""
+def debug_tc_plan(n_rows: int, kprime: int = 0, nq: int = 512, max_rounds: int = 16):
+    """Test hook: the rounds the tensor-core path runs for a shard of n_rows rows and nq queries (list of dicts, TC_PLAN_FIELDS)."""
     out = np.zeros((max_rounds, len(TC_PLAN_FIELDS)), dtype=np.int64)
-    n = load().fcs_debug_tc_plan(int(n_rows), int(kprime), _np_ptr(out), int(max_rounds))
+    n = load().fcs_debug_tc_plan(int(n_rows), int(kprime), int(nq), _np_ptr(out), int(max_rounds))
     if n < 0:
         _check(n)
     return [dict(zip(TC_PLAN_FIELDS, (int(v) for v in out[i]))) for i in range(n)]

@@ -1,0 +1,33 @@
+#!/bin/bash
+mkdir -p gpurun_out
+echo "== pytest (all gpu tests)"; timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -15
+run() {
+  local label=$1; shift
+  env "$@" timeout 300 python bench.py --no-cpu-baseline --no-extra $BARGS 2>gpurun_out/err_$label.log | python -c "
+import json,sys
+try:
+    d=json.loads(sys.stdin.read().strip().splitlines()[-1])
+    print('$label: %.3f ms/step  %.0f q/s  e2e %.0f  K3 frac %.3f  fallbacks %d launches %d' % (d['ms_per_step'], d['value'], d['e2e']['value'], d['roofline']['frac'], d['config']['tc_fallback_queries'], d['gpu_launches']))
+except Exception as e:
+    print('$label: FAILED', e)"
+  grep "fcs_tc\] phase" gpurun_out/err_$label.log | tail -${PH:-14}
+}
+BARGS="--workload cfg3 --steps 10 --warmup 3"
+PH=14 run base FCS_TC_PHASES=1
+PH=0 run base_nophase X=1
+PH=12 run r0_8 FCS_TC_R0_TILES=8 FCS_TC_PHASES=1
+PH=0 run r0_16 FCS_TC_R0_TILES=16
+PH=0 run cs256 FCS_TC_C_SAMPLE=256
+PH=0 run cs64m8 FCS_TC_C_SAMPLE=64 FCS_TC_M_MIN=8
+PH=0 run cs1024m8 FCS_TC_C_SAMPLE=1024 FCS_TC_M_MIN=8
+PH=0 run mf16 FCS_TC_M_FINAL=16
+PH=0 run mf40 FCS_TC_M_FINAL=40
+PH=0 run cf384 FCS_TC_CF_MIN=384 FCS_TC_CF_MULT=2.4
+BARGS="--workload cfg3 --nq 512 --steps 20 --warmup 3"
+PH=12 run nq512 FCS_TC_PHASES=1
+PH=0 run nq512_r0_8 FCS_TC_R0_TILES=8
+BARGS="--workload cfg3 --rows 1250000 --steps 20 --warmup 3"
+PH=12 run rows1.25M FCS_TC_PHASES=1
+PH=0 run rows1.25M_r0_8 FCS_TC_R0_TILES=8
+BARGS="--workload cfg4b --steps 5 --warmup 3"
+PH=14 run cfg4b FCS_TC_PHASES=1

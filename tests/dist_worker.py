@@ -29,6 +29,9 @@ def main():
             torch.cuda.synchronize()
             res[f"s_{tag}{qg}"] = s.cpu().numpy()
             res[f"i_{tag}{qg}"] = i.cpu().numpy()
+            # the end-to-end call (pinned host buffers, one sync) must give the same answer as the device-tensor call
+            sh, ih = eng.search_host(q.cpu().numpy(), k, mode=mode)
+            assert np.array_equal(ih, res[f"i_{tag}{qg}"]) and np.array_equal(sh, res[f"s_{tag}{qg}"]), f"search_host differs ({tag}, Q={qg})"
         eng.db.close()
     gathered = [None] * dist.get_world_size()
     dist.all_gather_object(gathered, {k_: v.tobytes() for k_, v in res.items()})

@@ -103,8 +103,8 @@ def test_tc_round_plan_visits_every_tile_exactly_once():
     from merizo_search_b200 import native
 
     for n_rows in (1, 100, 4096, 4097, 5000, 8191, 8192, 70001, 300000, 1_250_000, 3_333_333):
-        for kp in (64, 160, 512):
-            plan = native.debug_tc_plan(n_rows, kp)
+        for kp, nq in ((64, 1024), (160, 4096), (512, 65536)):
+            plan = native.debug_tc_plan(n_rows, kp, nq)
             nt = (n_rows + 127) // 128
             seen = []
             for r in plan:
