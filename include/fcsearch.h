@@ -128,6 +128,10 @@ int fcs_search_device(fcs_db* db, const float* q_dev, int nq, const int32_t* qle
  * buffers (which must still be valid) and waits.  *out_queued (optional) = length of that queue.
  * Cheap when there is nothing to do; fcs_search does this itself. */
 int fcs_search_finish(fcs_db* db, void* stream, int* out_queued);
+/* Enqueues on `stream` a copy of the last fcs_search_device's fallback-queue length (uint32) into DEVICE memory at
+ * dst_dev_u32, so that a multi-rank host can ship it with the key lists (one collective) and learn after its one
+ * synchronisation whether any rank has to call fcs_search_finish.  0 for searches without a queue. */
+int fcs_search_queue_len_to(fcs_db* db, void* dst_dev_u32, void* stream);
 
 /* cross-shard merge (replaces faiss.ResultHeap.add_result/finalize, dbsearch.py:224-245):
  *   keys_dev [n_lists][nq][k] packed keys from fcs_search_device of each shard (after the

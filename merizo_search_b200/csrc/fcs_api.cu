@@ -520,8 +520,6 @@ int fcs::api_search_core(fcs_db* db, const float* q_dev, int nq, const int32_t* 
     if (use_mode == FCS_MODE_AUTO) use_mode = api_auto_prefers_tc(db, nq, k, mask_on) ? FCS_MODE_TC : FCS_MODE_GEMV;
     if (use_mode == FCS_MODE_TC && mask_on)
         return FCS_FAIL(FCS_ERR_UNSUPPORTED, "FCS_MODE_TC does not apply the coverage mask (the faiss flavour has none, dbsearch.py:307-310)");
-    if (use_mode == FCS_MODE_TC && k > tc_max_k())
-        return FCS_FAIL(FCS_ERR_UNSUPPORTED, "FCS_MODE_TC supports k <= %d (got %d)", tc_max_k(), k);
     int launches = 0;
     if (db->profiling) FCS_CUDA(cudaEventRecord(db->ev0, stream));
     int rc = FCS_OK;
@@ -569,6 +567,17 @@ extern "C" int fcs_search_device(fcs_db* db, const float* q_dev, int nq, const i
         keys = db->d_keys;
     }
     return api_search_core(db, q_dev, nq, qlen, mincov, k, qnorm, mode, kprime, out_scores_dev, out_ids_dev, keys, st);
+}
+
+extern "C" int fcs_search_queue_len_to(fcs_db* db, void* dst_dev_u32, void* stream) {
+    if (!db || !dst_dev_u32) return FCS_FAIL(FCS_ERR_INVALID, "fcs_search_queue_len_to: NULL argument");
+    DeviceGuard guard(db->device);
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : db->stream;
+    if (db->pending.valid)
+        FCS_CUDA(cudaMemcpyAsync(dst_dev_u32, db->pending.q.count_dev, sizeof(unsigned), cudaMemcpyDeviceToDevice, st));
+    else
+        FCS_CUDA(cudaMemsetAsync(dst_dev_u32, 0, sizeof(unsigned), st));
+    return FCS_OK;
 }
 
 extern "C" int fcs_search_finish(fcs_db* db, void* stream, int* out_queued) {

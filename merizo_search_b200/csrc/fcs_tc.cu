@@ -79,10 +79,12 @@ constexpr int TC_PREFETCH = 6;                     // DB tiles prefetched into L
 constexpr int TC_RES_MAX = 16;                    // candidate slots reserved per atomic (upper bound, see res_block)
 constexpr int TC_MMA_WARPS = 4;                   // MMA-issuing warps (one thread each), one query tile apiece
 constexpr int TC_THREADS = (1 + TC_MMA_WARPS + 16) * 32;  // producer + MMA issuers + 16 epilogue warps
-constexpr int TC_CAP = 4096;                     // candidate slots per query
+constexpr int TC_CAP = 4096;                     // candidate slots per query (k' up to ~850)
+constexpr int TC_CAP_BIG = 16384;                // ... for larger k (up to FCS_MAX_K = 2048)
 constexpr int TC_R0_TILES = TC_CAP / TC_N;       // round 0 records every score of 32 tiles
 constexpr int TC_SMEM = TC_QT * A_TILE_BYTES + TC_STAGES * B_TILE_BYTES + 32 * 8 + 16;
-constexpr int TC_MAX_KPRIME = 512;
+constexpr int TC_MAX_KPRIME = 3328;               // k' for k = FCS_MAX_K
+constexpr int TC_WARP_K = 128;                    // k up to which the rescore keeps its top-k list in registers
 constexpr int TC_MAX_RANK = 1024;                // largest selection rank used for a threshold
 
 // Operand image layout (K-major, SWIZZLE_NONE "interleave" canonical layout, cute mma_sm100_desc):
@@ -263,7 +265,8 @@ struct TcGemmParams {
     int64_t n_idx, j0, stride, comp_T;
     const float* thr;      // [nq] approximate-score threshold (strict >)
     unsigned* cnt;         // [nq] append counters
-    uint64_t* cand;        // [nq][TC_CAP] approximate keys (score, LOCAL row); 0 = unused slot
+    uint64_t* cand;        // [nq][cap] approximate keys (score, LOCAL row); 0 = unused slot
+    int cap;               // candidate slots per query (TC_CAP or TC_CAP_BIG)
     int first_round;       // round 0: thresholds are -inf, slot = idx * 128 + column, no atomics
     int trace_on;          // debug builds (FCS_TC_TRACE): record cycle stamps in this launch
     int res_block;         // slots reserved per atomic: small when many CTAs share a query group (unused slots are waste)
@@ -292,21 +295,21 @@ __device__ long long g_trace[5][256];
 // y == ~0u: nothing reserved yet).  Deliberately NOT inlined: there are 32 call sites per 32-column part, and the
 // epilogue loop has to stay small enough for the instruction cache (an inlined append per column cost 3-5 k cycles
 // per hit in instruction-cache misses).
-__device__ __noinline__ uint2 tc_append(unsigned* cnt_q, uint64_t* cand_q, uint2 res, int res_block, uint32_t score_bits, uint32_t row) {
+__device__ __noinline__ uint2 tc_append(unsigned* cnt_q, uint64_t* cand_q, uint2 res, int res_block, uint32_t score_bits, uint32_t row, int cap) {
     if (res.y >= unsigned(res_block)) {
         res.x = atomicAdd(cnt_q, unsigned(res_block));
         res.y = 0;
     }
     const unsigned slot = res.x + res.y++;
-    if (slot < unsigned(TC_CAP)) cand_q[slot] = make_key(__uint_as_float(score_bits), row);
+    if (slot < unsigned(cap)) cand_q[slot] = make_key(__uint_as_float(score_bits), row);
     return res;
 }
 // unused slots of the last reservation must read as empty
-__device__ __forceinline__ void tc_close_reservation(uint64_t* cand_q, uint2 res, int res_block) {
+__device__ __forceinline__ void tc_close_reservation(uint64_t* cand_q, uint2 res, int res_block, int cap) {
     if (res.y == ~0u) return;  // this thread never appended
     for (; res.y < unsigned(res_block); ++res.y) {
         const unsigned slot = res.x + res.y;
-        if (slot < unsigned(TC_CAP)) cand_q[slot] = 0ull;
+        if (slot < unsigned(cap)) cand_q[slot] = 0ull;
     }
 }
 
@@ -438,7 +441,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_filter_kernel(const TcG
             const float thr = (q < p.nq) ? p.thr[q] : INFINITY;
             const int qc = q < p.nq ? q : 0;
             unsigned* cnt_q = p.cnt + qc;
-            uint64_t* cand_q = p.cand + size_t(qc) * TC_CAP;
+            uint64_t* cand_q = p.cand + size_t(qc) * p.cap;
             uint2 res = make_uint2(0u, ~0u);
             for (int64_t j = 0; j < seg_len; ++j, ++it) {
                 const uint32_t tph = it & 1u;
@@ -500,7 +503,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_filter_kernel(const TcG
                                     for (int c = 0; c < 8; ++c) {
                                         const int col = part * 32 + g * 8 + c;
                                         if (f[g * 8 + c] > thr && col < rows_here)
-                                            res = tc_append(cnt_q, cand_q, res, p.res_block, r[g * 8 + c], uint32_t(row_base) + uint32_t(col));
+                                            res = tc_append(cnt_q, cand_q, res, p.res_block, r[g * 8 + c], uint32_t(row_base) + uint32_t(col), p.cap);
                                     }
                                 }
                             }
@@ -545,7 +548,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_filter_kernel(const TcG
 #pragma unroll
                                 for (int cc = 1; cc < 8; ++cc) bits = (c == cc) ? v8[cc] : bits;
                                 const int col = part * 32 + g * 8 + c;
-                                if (col < rows_here) res = tc_append(cnt_q, cand_q, res, p.res_block, bits, uint32_t(row_base) + uint32_t(col));
+                                if (col < rows_here) res = tc_append(cnt_q, cand_q, res, p.res_block, bits, uint32_t(row_base) + uint32_t(col), p.cap);
                             }
                         }
                     }
@@ -557,7 +560,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_filter_kernel(const TcG
                 if (lane == 0) mbar_arrive(&tmem_empty[t]);
                 TRACE(4, it, blockIdx.x == 0 && warp == 5 && lane == 0);
             }
-            if (!p.first_round) tc_close_reservation(cand_q, res, p.res_block);
+            if (!p.first_round) tc_close_reservation(cand_q, res, p.res_block, p.cap);
             s += seg_len;
         }
     }
@@ -589,6 +592,7 @@ struct TcSelectParams {
     unsigned* flags;
     int rank;
     int partition;
+    int cap;
 };
 
 // Radix select in shared memory: the candidates of one query (<= 4096 keys, 32 KB) are staged once; the bits on which
@@ -597,18 +601,18 @@ struct TcSelectParams {
 // pass costs three barriers.  Scores of one query's candidates share their upper bits (same sign, 1-2 exponents): 3
 // passes are typical.
 __global__ void __launch_bounds__(SEL_NT) tc_select_kernel(const TcSelectParams p) {
-    __shared__ uint64_t s_key[TC_CAP];
+    extern __shared__ uint64_t s_key[];  // [cap]
     __shared__ int s_hist[256];
     __shared__ uint32_t s_part[3][SEL_NT / 32];
     __shared__ int s_misc[4];  // [0] digit, [1] remaining rank, [2] survivors written, [3] others written
     const int q = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     unsigned raw = p.cnt[q];
-    if (raw > unsigned(TC_CAP)) {  // candidates were lost: the query goes to the exact scan in the end
+    if (raw > unsigned(p.cap)) {  // candidates were lost: the query goes to the exact scan in the end
         if (tid == 0) atomicOr(p.flags + q, 1u);
-        raw = unsigned(TC_CAP);
+        raw = unsigned(p.cap);
     }
     const int n = int(raw);
-    uint64_t* base = p.cand + size_t(q) * TC_CAP;
+    uint64_t* base = p.cand + size_t(q) * p.cap;
     uint32_t lmin = 0xFFFFFFFFu, lmax = 0u, real = 0u;
     for (int i = tid; i < n; i += SEL_NT) {
         const uint64_t key = base[i];
@@ -727,7 +731,8 @@ struct TcRescoreParams {
     const float* rows;      // fp32 row-swizzled shard
     const float* qn;        // [nq][128] normalised queries
     const float* q_raw;     // [nq][128] queries as given (copied to the fallback queue)
-    const uint64_t* cand;   // [nq][TC_CAP] approximate keys: [0, sel_cnt) the k' best, [sel_cnt, cnt) the rest
+    const uint64_t* cand;   // [nq][cap] approximate keys: [0, sel_cnt) the k' best, [sel_cnt, cnt) the rest
+    int cap;
     const unsigned* cnt;
     const unsigned* sel_cnt;
     const float* eps;       // [nq] certificate slack
@@ -812,7 +817,7 @@ __global__ void __launch_bounds__(128) tc_rescore_kernel(const TcRescoreParams p
     const int n_all = int(p.cnt[q]);
     const int n_sel = int(p.sel_cnt[q]);
     const unsigned fl = p.flags[q];
-    const uint64_t* cand = p.cand + size_t(q) * TC_CAP;
+    const uint64_t* cand = p.cand + size_t(q) * p.cap;
     const float4* q4 = reinterpret_cast<const float4*>(p.qn + size_t(q) * DIM);
     const float eps = p.eps[q];
     WarpTopK<4> tk;
@@ -874,6 +879,115 @@ __global__ void __launch_bounds__(128) tc_rescore_kernel(const TcRescoreParams p
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// K4 for k > 128 (up to FCS_MAX_K): one block per query.  The exact keys of the candidates are written to shared
+// memory and sorted there (bitonic, descending); same two-phase certificate, same fallback queue.
+// ------------------------------------------------------------------------------------------------
+constexpr int RB_NT = 256;
+
+__device__ __forceinline__ void rb_exact_keys(const TcRescoreParams& p, const uint64_t* cand, const float4* q4, int c_begin, int c_end,
+                                              uint64_t* s_keys, int warp, int lane) {
+    constexpr int U = 4;  // candidate rows in flight per warp
+    for (int c0 = c_begin + warp * U; c0 < c_end; c0 += (RB_NT / 32) * U) {
+        float part[U];
+        int64_t rowid[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            part[u] = 0.f;
+            rowid[u] = -1;
+            if (c0 + u < c_end) {
+                const int64_t row = key_id(cand[c0 + u]);
+                rowid[u] = row;
+                if (row >= 0) {
+                    const float4 v = reinterpret_cast<const float4*>(p.rows + row * DIM)[lane];
+                    const float4 w = q4[swz_chunk(lane, row)];
+                    part[u] = fmaf(v.w, w.w, fmaf(v.z, w.z, fmaf(v.y, w.y, v.x * w.x)));
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            float sacc = part[u];
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1) sacc += __shfl_xor_sync(FULL, sacc, o);
+            if (lane == 0 && c0 + u < c_end) s_keys[c0 + u] = rowid[u] >= 0 ? make_key(sacc, p.id_base + uint32_t(rowid[u])) : 0ull;
+        }
+    }
+}
+
+// sorts s_keys[0, n) descending (pads to a power of two with empty keys); all RB_NT threads call
+__device__ __forceinline__ void rb_sort_desc(uint64_t* s_keys, int n, int tid) {
+    int P = 2;
+    while (P < n) P <<= 1;
+    for (int i = n + tid; i < P; i += RB_NT) s_keys[i] = 0ull;
+    __syncthreads();
+    for (int size = 2; size <= P; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int i = tid; i < (P >> 1); i += RB_NT) {
+                const int lo = ((i & ~(stride - 1)) << 1) | (i & (stride - 1));
+                const int hi = lo + stride;
+                const bool desc = (lo & size) == 0;
+                const uint64_t a = s_keys[lo], b = s_keys[hi];
+                if ((a < b) == desc) {
+                    s_keys[lo] = b;
+                    s_keys[hi] = a;
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(RB_NT) tc_rescore_big_kernel(const TcRescoreParams p) {
+    extern __shared__ uint64_t s_keys[];  // [cap]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int q = blockIdx.x;
+    const int n_all = int(p.cnt[q]);
+    const int n_sel = int(p.sel_cnt[q]);
+    const unsigned fl = p.flags[q];
+    const uint64_t* cand = p.cand + size_t(q) * p.cap;
+    const float4* q4 = reinterpret_cast<const float4*>(p.qn + size_t(q) * DIM);
+    const float eps = p.eps[q];
+    // Phase A (see tc_rescore_kernel): the k' best approximate candidates
+    rb_exact_keys(p, cand, q4, 0, n_sel, s_keys, warp, lane);
+    __syncthreads();
+    rb_sort_desc(s_keys, n_sel, tid);
+    int n_have = n_sel;
+    bool ok = false;
+    if (!(fl & 1u)) {
+        const float tprime = p.thr_sel[q];
+        const float sk = n_have >= p.k ? key_score(s_keys[p.k - 1]) : -INFINITY;
+        ok = (tprime == -INFINITY) || (sk > tprime + eps);
+        if (!ok && n_all > n_sel) {  // Phase B: every row above the sweep threshold (block-uniform decision)
+            __syncthreads();
+            rb_exact_keys(p, cand, q4, n_sel, n_all, s_keys, warp, lane);
+            __syncthreads();
+            rb_sort_desc(s_keys, n_all, tid);
+            n_have = n_all;
+            const float tround = p.thr[q];
+            const float sk2 = n_have >= p.k ? key_score(s_keys[p.k - 1]) : -INFINITY;
+            ok = (tround == -INFINITY) || (sk2 > tround + eps);
+        }
+    }
+    if (!ok && warp == 0) {
+        unsigned slot = 0;
+        if (lane == 0) {
+            slot = atomicAdd(p.n_flagged, 1u);
+            p.fb_list[slot] = q;
+            p.flags[q] = fl | 2u;
+        }
+        slot = __shfl_sync(FULL, slot, 0);
+        reinterpret_cast<float4*>(p.fb_q + size_t(slot) * DIM)[lane] = reinterpret_cast<const float4*>(p.q_raw + size_t(q) * DIM)[lane];
+    }
+    const size_t base = size_t(q) * p.k;
+    for (int r = tid; r < p.k; r += RB_NT) {
+        const uint64_t key = r < n_have ? s_keys[r] : 0ull;
+        p.out_keys[base + r] = key;
+        if (p.out_scores) p.out_scores[base + r] = key_score(key);
+        if (p.out_ids) p.out_ids[base + r] = key_id(key);
+    }
+}
+
 thread_local std::string g_tc_error;
 int tc_fail(int code, const char* what, cudaError_t e) {
     g_tc_error = std::string(what) + ": " + cudaGetErrorString(e);
@@ -915,6 +1029,7 @@ struct TcState {
     float max_rhat = 1.f, max_dr = 0.f;
     // per-search workspace, grown on demand
     int nq_cap = 0;
+    size_t cand_elems = 0;  // keys the candidate buffer holds
     float* qn = nullptr;
     uint8_t* a_img = nullptr;
     float* thr = nullptr;
@@ -1016,7 +1131,7 @@ void tc_phase_mark(TcState* s, const char* label, cudaStream_t stream) {
 
 const char* tc_last_error() { return g_tc_error.c_str(); }
 int tc_min_batch() { return 32; }
-int tc_max_k() { return 128; }
+int tc_max_k() { return FCS_MAX_K; }
 int tc_last_rounds(const TcState* s) { return s ? s->last_rounds : 0; }
 uint64_t tc_image_bytes(const TcState* s) { return s ? uint64_t(s->n_tiles) * B_TILE_BYTES : 0; }
 
@@ -1051,6 +1166,7 @@ static void tc_free_workspace(TcState* s) {
     s->qn = nullptr; s->a_img = nullptr; s->thr = nullptr; s->thr_sel = nullptr; s->cnt = nullptr; s->sel_cnt = nullptr;
     s->cand = nullptr; s->flags = nullptr; s->eps = nullptr; s->fb_list = nullptr; s->fb_q = nullptr;
     s->nq_cap = 0;
+    s->cand_elems = 0;
 }
 
 void tc_destroy(TcState* s) {
@@ -1089,7 +1205,10 @@ int tc_create(TcState** out, int device, int sm_count, const float* rows, int64_
         TC_CUDA(cudaFuncSetAttribute(tc_gemm_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
         // the small kernels between two GEMM launches ask for the same shared-memory carve-out as the GEMM kernel,
         // so the SMs are not reconfigured (drained) twice per round
+        TC_CUDA(cudaFuncSetAttribute(tc_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_CAP_BIG * 8));
+        TC_CUDA(cudaFuncSetAttribute(tc_rescore_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_CAP_BIG * 8));
         TC_CUDA(cudaFuncSetAttribute(tc_select_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        TC_CUDA(cudaFuncSetAttribute(tc_rescore_big_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         TC_CUDA(cudaFuncSetAttribute(tc_prep_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         TC_CUDA(cudaFuncSetAttribute(tc_rescore_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         TC_CUDA(cudaFuncSetAttribute(tc_rescore_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -1123,10 +1242,23 @@ int tc_create(TcState** out, int device, int sm_count, const float* rows, int64_
     return FCS_OK;
 }
 
-static int tc_ensure_workspace(TcState* s, int nq) {
-    if (nq <= s->nq_cap) return FCS_OK;
+static int tc_ensure_workspace(TcState* s, int nq, int cap) {
+    const int nq_pad_want = ((nq + TC_QGROUP - 1) / TC_QGROUP) * TC_QGROUP;
+    if (nq <= s->nq_cap && size_t(nq_pad_want) * size_t(cap) <= s->cand_elems) return FCS_OK;
+    if (size_t(nq_pad_want) * size_t(cap) * 8 > (size_t(24) << 30)) {
+        g_tc_error = "candidate buffers of this batch would exceed 24 GB: split the batch (large k with a very large batch)";
+        return FCS_ERR_NOMEM;
+    }
+    if (nq <= s->nq_cap) {  // only the candidate buffer has to grow (a larger k than before)
+        cudaFree(s->cand);
+        s->cand = nullptr;
+        s->cand_elems = 0;
+        TC_CUDA(cudaMalloc(&s->cand, size_t(s->nq_cap) * size_t(cap) * 8));
+        s->cand_elems = size_t(s->nq_cap) * size_t(cap);
+        return FCS_OK;
+    }
     tc_free_workspace(s);
-    const int nq_pad = ((nq + TC_QGROUP - 1) / TC_QGROUP) * TC_QGROUP;
+    const int nq_pad = nq_pad_want;
     TC_CUDA(cudaMalloc(&s->qn, size_t(nq_pad) * DIM * 4));
     TC_CUDA(cudaMalloc(&s->a_img, size_t(nq_pad / TC_M) * A_TILE_BYTES));
     TC_CUDA(cudaMalloc(&s->thr, size_t(nq_pad) * 4));
@@ -1137,15 +1269,19 @@ static int tc_ensure_workspace(TcState* s, int nq) {
     TC_CUDA(cudaMalloc(&s->eps, size_t(nq_pad) * 4));
     TC_CUDA(cudaMalloc(&s->fb_list, size_t(nq_pad) * 4));
     TC_CUDA(cudaMalloc(&s->fb_q, size_t(nq_pad) * DIM * 4));
-    TC_CUDA(cudaMalloc(&s->cand, size_t(nq_pad) * TC_CAP * 8));
+    TC_CUDA(cudaMalloc(&s->cand, size_t(nq_pad) * size_t(cap) * 8));
+    s->cand_elems = size_t(nq_pad) * size_t(cap);
     s->nq_cap = nq_pad;
     return FCS_OK;
 }
 
 int tc_default_kprime(int k) {
-    // margin for the exactness certificate: eps (~0.0035 for unit vectors) covers a few dozen ranks at TED scale
-    int kp = k + (k * 6 / 10 > 32 ? k * 6 / 10 : 32);
-    kp = (kp + 31) / 32 * 32;
+    // margin for the exactness certificate: eps (~0.0035 for unit vectors) covers a few dozen ranks at TED scale;
+    // 60 % of k for small k, 256 + k/4 for large k (the ranks get denser further down the list)
+    int margin = k * 6 / 10;
+    if (margin > 256 + k / 4) margin = 256 + k / 4;
+    if (margin < 32) margin = 32;
+    int kp = (k + margin + 31) / 32 * 32;
     return kp > TC_MAX_KPRIME ? TC_MAX_KPRIME : kp;
 }
 
@@ -1158,11 +1294,11 @@ static void tc_launch_prep(TcState* s, const float* q_dev, int nq, int nq_pad, i
     tc_prep_kernel<<<(nq_pad + 3) / 4, 128, 0, stream>>>(pp);
 }
 
-static void tc_launch_gemm(TcState* s, const TcRound& r, int nq, int n_qgroups, cudaStream_t stream, int trace_on) {
+static void tc_launch_gemm(TcState* s, const TcRound& r, int nq, int n_qgroups, int cap, cudaStream_t stream, int trace_on) {
     TcGemmParams gp = {};
     gp.a_img = s->a_img; gp.b_img = s->b_img; gp.n_rows = s->n_rows; gp.nq = nq; gp.n_qgroups = n_qgroups;
     gp.n_idx = r.n_idx; gp.j0 = r.j0; gp.stride = r.stride; gp.comp_T = r.comp_T;
-    gp.thr = s->thr; gp.cnt = s->cnt; gp.cand = s->cand; gp.first_round = r.first; gp.trace_on = trace_on;
+    gp.thr = s->thr; gp.cnt = s->cnt; gp.cand = s->cand; gp.cap = cap; gp.first_round = r.first; gp.trace_on = trace_on;
     const int64_t steps = int64_t(n_qgroups) * r.n_idx;
     const int grid = int(steps < s->sm_count ? steps : s->sm_count);
     // every thread that appends at all rounds its reservation up to res_block slots: keep the waste of the
@@ -1185,7 +1321,11 @@ int tc_search(TcState* s, const float* q_dev, int nq, int k, int kprime, int qno
     int kp = kprime > 0 ? kprime : tc_default_kprime(k);
     if (kp < k) kp = k;
     if (kp > TC_MAX_KPRIME) kp = TC_MAX_KPRIME;
-    int rc = tc_ensure_workspace(s, nq);
+    // candidate slots per query: the sweep leaves about cf rows above its threshold (+- 50 %), plus the kept sample ranks
+    // and the unused ends of slot reservations
+    const double cf = std::fmax(s->cf_mult * kp, s->cf_min);
+    const int cap = (1.6 * cf + 600.0 > double(TC_CAP)) ? TC_CAP_BIG : TC_CAP;
+    int rc = tc_ensure_workspace(s, nq, cap);
     if (rc != FCS_OK) return rc;
     const int n_qgroups = (nq + TC_QGROUP - 1) / TC_QGROUP;
     const int nq_pad = n_qgroups * TC_QGROUP;
@@ -1207,12 +1347,12 @@ int tc_search(TcState* s, const float* q_dev, int nq, int k, int kprime, int qno
         const bool timed = rounds < TcState::MAX_ROUNDS;
         tc_phase(s, r.first ? "gemm-dump" : (r.comp_T ? "gemm-sweep" : "gemm-sample"), stream);
         if (timed) TC_CUDA(cudaEventRecord(s->ev[2 * rounds], stream));
-        tc_launch_gemm(s, r, nq, n_qgroups, stream, trace_round == rounds ? 1 : 0);
+        tc_launch_gemm(s, r, nq, n_qgroups, cap, stream, trace_round == rounds ? 1 : 0);
         TC_CUDA(cudaGetLastError());
         if (timed) TC_CUDA(cudaEventRecord(s->ev[2 * rounds + 1], stream));
         tc_phase(s, "select", stream);
-        TcSelectParams sp = {s->cand, s->cnt, s->thr, s->thr_sel, s->sel_cnt, s->flags, r.rank, r.partition};
-        tc_select_kernel<<<nq, SEL_NT, 0, stream>>>(sp);
+        TcSelectParams sp = {s->cand, s->cnt, s->thr, s->thr_sel, s->sel_cnt, s->flags, r.rank, r.partition, cap};
+        tc_select_kernel<<<nq, SEL_NT, size_t(cap) * 8, stream>>>(sp);
         TC_CUDA(cudaGetLastError());
         *launches += 2;
         if (s->verbose)
@@ -1225,10 +1365,11 @@ int tc_search(TcState* s, const float* q_dev, int nq, int k, int kprime, int qno
     TcRescoreParams rp = {};
     rp.rows = s->rows; rp.qn = s->qn; rp.q_raw = q_dev; rp.cand = s->cand; rp.cnt = s->cnt; rp.sel_cnt = s->sel_cnt;
     rp.eps = s->eps; rp.thr = s->thr; rp.thr_sel = s->thr_sel; rp.flags = s->flags; rp.n_flagged = s->n_flagged;
-    rp.fb_list = s->fb_list; rp.fb_q = s->fb_q; rp.nq = nq; rp.k = k; rp.id_base = s->id_base;
+    rp.fb_list = s->fb_list; rp.fb_q = s->fb_q; rp.nq = nq; rp.k = k; rp.id_base = s->id_base; rp.cap = cap;
     rp.out_keys = out_keys; rp.out_scores = out_scores; rp.out_ids = out_ids;
     tc_phase(s, "rescore", stream);
-    if (nq <= 2048) tc_rescore_kernel<4><<<nq, 128, 0, stream>>>(rp);
+    if (k > TC_WARP_K) tc_rescore_big_kernel<<<nq, RB_NT, size_t(cap) * 8, stream>>>(rp);
+    else if (nq <= 2048) tc_rescore_kernel<4><<<nq, 128, 0, stream>>>(rp);
     else tc_rescore_kernel<1><<<(nq + 3) / 4, 128, 0, stream>>>(rp);
     TC_CUDA(cudaGetLastError());
     ++*launches;
@@ -1291,14 +1432,14 @@ int tc_debug_approx(TcState* s, const float* q_dev, int nq, int qnorm, float* ou
         g_tc_error = "tc_debug_approx: shard larger than the candidate buffer";
         return FCS_ERR_UNSUPPORTED;
     }
-    int rc = tc_ensure_workspace(s, nq);
+    int rc = tc_ensure_workspace(s, nq, TC_CAP);
     if (rc != FCS_OK) return rc;
     const int n_qgroups = (nq + TC_QGROUP - 1) / TC_QGROUP;
     const int nq_pad = n_qgroups * TC_QGROUP;
     tc_launch_prep(s, q_dev, nq, nq_pad, qnorm, unsigned(s->n_tiles * TC_N), stream);
     TC_CUDA(cudaGetLastError());
     const TcRound r0 = {s->n_tiles, 0, 1, 0, 1, 1, 0};
-    tc_launch_gemm(s, r0, nq, n_qgroups, stream, 0);
+    tc_launch_gemm(s, r0, nq, n_qgroups, TC_CAP, stream, 0);
     TC_CUDA(cudaGetLastError());
     TC_CUDA(cudaStreamSynchronize(stream));
     std::string keys(size_t(nq) * TC_CAP * 8, '\0');

@@ -206,6 +206,7 @@ class DistributedEngine:
         self._side = None
         self._pinned = None
         self._last_keys = None
+        self._last_queue_max = None
         self.db: Optional[native.Database] = None
         if create_handle:
             self.db = native.Database(self.row1 - self.row0, device=self.device, id_offset=self.row0,
@@ -232,34 +233,41 @@ class DistributedEngine:
         lo = min(nq, self.q_index * per)
         return lo, min(nq, lo + per), per
 
-    def local_keys(self, q_dev, nq: int, k: int, qlen=None, **kw):
-        """This rank's [nq,k] packed keys (torch int64 CUDA tensor viewing uint64 keys)."""
+    def local_keys(self, q_dev, nq: int, k: int, qlen=None, rows: Optional[int] = None, **kw):
+        """This rank's packed keys (torch int64 CUDA tensor viewing uint64 keys): `rows` rows (default nq), the first nq
+        hold the shard's [nq,k] sorted lists.  With rows > nq, row `rows-1` carries the length of the search's exact-scan
+        fallback queue in its first word (fcs_search_queue_len_to): it travels with the keys in the one all-gather."""
         import torch
 
+        rows = nq if rows is None else rows
         dev = torch.device("cuda", self.dev_index)
-        keys = torch.zeros((nq, k), dtype=torch.int64, device=dev)
+        keys = torch.zeros((rows, k), dtype=torch.int64, device=dev)
         cur = torch.cuda.current_stream(dev)
-        if cur.cuda_stream != 0:
-            self.db.search_device(q_dev.data_ptr(), nq, k, 0, 0, out_keys_ptr=keys.data_ptr(), stream=cur.cuda_stream, qlen=qlen, **kw)
-        else:
+        st = cur
+        if cur.cuda_stream == 0:
             # the library reads stream 0 as "the handle's own stream": never launch on the legacy default stream,
             # use a side stream ordered after what produced the queries and before what consumes the keys
             if self._side is None:
                 self._side = torch.cuda.Stream(dev)
             self._side.wait_stream(cur)
-            self.db.search_device(q_dev.data_ptr(), nq, k, 0, 0, out_keys_ptr=keys.data_ptr(), stream=self._side.cuda_stream,
-                                  qlen=qlen, **kw)
-            cur.wait_stream(self._side)
+            st = self._side
+        if nq > 0:
+            self.db.search_device(q_dev.data_ptr(), nq, k, 0, 0, out_keys_ptr=keys.data_ptr(), stream=st.cuda_stream, qlen=qlen, **kw)
+            if rows > nq:
+                self.db.queue_len_to(keys[rows - 1].data_ptr(), stream=st.cuda_stream)
+        if st is not cur:
+            cur.wait_stream(st)
         return keys
 
     def search_host(self, q_host, k: int, **kw):
         """Host arrays in (the same queries on every rank), host arrays out: H2D copy from pinned memory, shard search,
-        NCCL key all-gather, GPU merge, D2H copy into pinned memory -- one host synchronisation.  This is the end-to-end
-        call of the one-rank-per-GPU deployment.  Exact on every rank: if some rank had to defer part of its exact-scan
-        fallback queue (more than ASYNC_FALLBACK_QUERIES queries failed their certificate), all ranks learn it through a
-        one-word all-reduce and the exchange + merge is repeated."""
+        NCCL key all-gather, GPU merge, D2H copy into pinned memory -- ONE host synchronisation and ONE collective.  This is
+        the end-to-end call of the one-rank-per-GPU deployment.  The returned arrays are views of pinned buffers owned by the
+        engine (valid until the next call).  Exact on every rank: the length of every rank's exact-scan fallback queue rides
+        along with the keys; if some rank had to defer part of its queue (more than ASYNC_FALLBACK_QUERIES queries failed
+        their certificate: pathological data), every rank sees it after the synchronisation and the exchange + merge is
+        repeated on the completed lists."""
         import torch
-        import torch.distributed as dist
 
         dev = torch.device("cuda", self.dev_index)
         qh = torch.as_tensor(q_host, dtype=torch.float32).reshape(-1, DIM)
@@ -269,7 +277,7 @@ class DistributedEngine:
             pin = self._pinned = {"q": torch.empty((nq, DIM), dtype=torch.float32).pin_memory(), "k": k,
                                   "sc": torch.empty((nq, k), dtype=torch.float32).pin_memory(),
                                   "ids": torch.empty((nq, k), dtype=torch.int64).pin_memory(),
-                                  "flag": torch.zeros(1, dtype=torch.int32, device=dev)}
+                                  "flag": torch.zeros(1, dtype=torch.int64).pin_memory()}
         if qh.is_pinned():
             src = qh
         else:
@@ -281,23 +289,25 @@ class DistributedEngine:
             sc, ids = self.search(q_dev, k, **kw)
             pin["sc"][:nq].copy_(sc, non_blocking=True)
             pin["ids"][:nq].copy_(ids, non_blocking=True)
+            if self._last_queue_max is not None:
+                pin["flag"].copy_(self._last_queue_max, non_blocking=True)
+            else:
+                pin["flag"].zero_()
             cur.synchronize()
-            deferred = 0
-            if self.db is not None:
-                deferred = 1 if self.db.search_finish(cur.cuda_stream) > native.ASYNC_FALLBACK_QUERIES else 0
-            if self.world > 1 and dist.is_initialized():
-                pin["flag"].fill_(deferred)
-                dist.all_reduce(pin["flag"], op=dist.ReduceOp.MAX)
-                deferred = int(pin["flag"].item())
-            if not deferred:
+            if int(pin["flag"][0]) <= native.ASYNC_FALLBACK_QUERIES:
                 break
-            # the finished shard lists are in place now: a second pass re-runs the (idempotent) exchange on complete lists
+            # some rank deferred part of its queue: every rank finishes its own (a no-op for most), then the (idempotent)
+            # exchange + merge is repeated on the completed lists
+            if self.db is not None:
+                self.db.search_finish(cur.cuda_stream)
             kw = dict(kw, _reuse_local=True)
-        return pin["sc"][:nq].numpy().copy(), pin["ids"][:nq].numpy().copy()
+        return pin["sc"][:nq].numpy(), pin["ids"][:nq].numpy()
 
     def search(self, q_dev, k: int, local_search=None, merge=None, qlen=None, _reuse_local=False, **kw):
         """Replicated queries in, identical (scores, ids) on every rank out (torch tensors).  Asynchronous on the current
-        stream: nothing here waits for the host."""
+        stream: nothing here waits for the host.  ``self._last_queue_max`` (a 1-element device tensor, or None when the
+        shard search is injected) is the longest exact-scan fallback queue over all ranks; callers that need the exactness
+        guarantee under pathological data check it after their synchronisation (search_host does)."""
         import torch
         import torch.distributed as dist
 
@@ -305,32 +315,39 @@ class DistributedEngine:
         lo, hi, per = self.query_slice(nq)
         q_mine = q_dev[lo:hi]
         ql_mine = None if qlen is None else np.asarray(qlen)[lo:hi]
+        carry = local_search is None and self.db is not None  # one extra key row per rank carries the queue length
+        rows = per + 1 if carry else per
         if _reuse_local and self._last_keys is not None:
             keys = self._last_keys  # the previous call's shard list, completed in place by search_finish
-        elif hi - lo > 0:
-            if local_search:
-                keys = local_search(q_mine, hi - lo, k)
-            else:
-                keys = self.local_keys(q_mine, hi - lo, k, qlen=ql_mine, **kw)
+            if carry:
+                keys[rows - 1].zero_()
+        elif carry:
+            keys = self.local_keys(q_mine, hi - lo, k, qlen=ql_mine, rows=rows, **kw)
         else:
-            keys = torch.zeros((0, k), dtype=torch.int64, device=q_dev.device)
+            keys = local_search(q_mine, hi - lo, k) if hi - lo > 0 else torch.zeros((0, k), dtype=torch.int64, device=q_dev.device)
+            if hi - lo < per:  # pad the slice: every rank contributes the same shape; key 0 = empty
+                keys = torch.cat([keys, torch.zeros((per - (hi - lo), k), dtype=torch.int64, device=keys.device)], dim=0)
         self._last_keys = keys
-        if hi - lo < per:  # pad the slice: every rank contributes the same shape; key 0 = empty
-            pad = torch.zeros((per - (hi - lo), k), dtype=torch.int64, device=keys.device)
-            keys = torch.cat([keys, pad], dim=0)
-        gathered = torch.empty((self.world, per, k), dtype=keys.dtype, device=keys.device)
-        # the one collective on the path: 8 B per entry (flat [world*per, k] view: the layout gloo and nccl both accept)
-        dist.all_gather_into_tensor(gathered.view(self.world * per, k), keys.contiguous())
-        # rank = r*Q + j  =>  gathered is [R][Q*per][k]: R sorted lists for each of the Q*per (padded) queries
-        lists = gathered.view(self.row_shards, self.q_groups * per, k)
+        gathered = torch.empty((self.world, rows, k), dtype=keys.dtype, device=keys.device)
+        # the one collective on the path: 8 B per entry (flat [world*rows, k] view: the layout gloo and nccl both accept)
+        dist.all_gather_into_tensor(gathered.view(self.world * rows, k), keys.contiguous())
+        # rank = r*Q + j  =>  gathered is [R][Q*rows][k]: R sorted lists for each of the Q*rows (padded) query rows
+        lists = gathered.view(self.row_shards, self.q_groups * rows, k)
         if merge:
             sc, ids = merge(lists, k)
         else:
-            sc = torch.empty((self.q_groups * per, k), dtype=torch.float32, device=keys.device)
-            ids = torch.empty((self.q_groups * per, k), dtype=torch.int64, device=keys.device)
+            sc = torch.empty((self.q_groups * rows, k), dtype=torch.float32, device=keys.device)
+            ids = torch.empty((self.q_groups * rows, k), dtype=torch.int64, device=keys.device)
             st = torch.cuda.current_stream(keys.device)
-            native.merge_topk(self.dev_index, lists.data_ptr(), self.row_shards, self.q_groups * per, k, sc.data_ptr(),
+            native.merge_topk(self.dev_index, lists.data_ptr(), self.row_shards, self.q_groups * rows, k, sc.data_ptr(),
                               ids.data_ptr(), stream=st.cuda_stream)
+        self._last_queue_max = None
+        if carry:
+            # drop the carrier rows (merged garbage) and keep the longest queue length any rank reported
+            self._last_queue_max = (gathered[:, rows - 1, 0] & 0xFFFFFFFF).max().reshape(1)
+            if self.q_groups > 1:
+                sc = sc.view(self.q_groups, rows, k)[:, :per].reshape(self.q_groups * per, k)
+                ids = ids.view(self.q_groups, rows, k)[:, :per].reshape(self.q_groups * per, k)
         return sc[:nq], ids[:nq]
 
 

@@ -26,7 +26,7 @@ EMBED_MODE_FP32, EMBED_MODE_TC = 0, 1
 EXPORTS = [
     "fcs_version", "fcs_last_error", "fcs_device_count", "fcs_db_create", "fcs_db_upload",
     "fcs_db_upload_device", "fcs_db_finalize", "fcs_db_get_info", "fcs_db_destroy", "fcs_search",
-    "fcs_search_device", "fcs_search_finish", "fcs_merge_topk", "fcs_get_timing", "fcs_set_profiling", "fcs_debug_tc_approx",
+    "fcs_search_device", "fcs_search_finish", "fcs_search_queue_len_to", "fcs_merge_topk", "fcs_get_timing", "fcs_set_profiling", "fcs_debug_tc_approx",
     "fcs_debug_tc_plan", "fcs_debug_tc_tile_of", "fcs_db_upload_file",
     "fcs_group_create", "fcs_group_upload", "fcs_group_upload_file", "fcs_group_finalize", "fcs_group_search",
     "fcs_group_get_info", "fcs_group_shard", "fcs_group_last_fallbacks", "fcs_group_destroy",
@@ -107,6 +107,7 @@ def load() -> C.CDLL:
     lib.fcs_search.argtypes = [vp, vp, i32, vp, f32, i32, i32, i32, i32, vp, vp]
     lib.fcs_search_device.argtypes = [vp, vp, i32, vp, f32, i32, i32, i32, i32, vp, vp, vp, vp]
     lib.fcs_search_finish.argtypes = [vp, vp, C.POINTER(C.c_int)]
+    lib.fcs_search_queue_len_to.argtypes = [vp, vp, vp]
     lib.fcs_debug_tc_plan.argtypes = [i64, i32, i32, vp, i32]
     lib.fcs_debug_tc_tile_of.argtypes = [i64, i64, i64, i64]
     lib.fcs_merge_topk.argtypes = [i32, vp, i32, i32, i32, vp, vp, vp]
@@ -209,6 +210,10 @@ class Database:
         n = C.c_int(0)
         _check(self._lib.fcs_search_finish(self._h, C.c_void_p(stream) if stream else None, C.byref(n)))
         return n.value
+
+    def queue_len_to(self, dst_ptr: int, stream: int = 0) -> None:
+        """Enqueue a copy of the last asynchronous search's fallback-queue length (uint32) to device memory at dst_ptr."""
+        _check(self._lib.fcs_search_queue_len_to(self._h, C.c_void_p(dst_ptr), C.c_void_p(stream) if stream else None))
 
     def debug_tc_approx(self, q: np.ndarray, qnorm: int = QNORM_NONE) -> np.ndarray:
         """Test hook: bf16 tensor-core scores [nq, n_rows] (shards of <= 4096 rows)."""

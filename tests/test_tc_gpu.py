@@ -49,6 +49,28 @@ def test_tc_search_is_exact(n, nq, k):
     h.close()
 
 
+@pytest.mark.parametrize("n,nq,k", [(200000, 96, 129), (200000, 70, 500), (400000, 40, 2048), (60000, 33, 1000)])
+def test_tc_search_large_k_is_exact(n, nq, k):
+    """k above the register-resident list size (128) and up to FCS_MAX_K: larger candidate buffers, the block-sort rescore,
+    multi-pass exact scan for the fallback queue.  `-k` is unbounded in the reference (merizo.py:134)."""
+    db = synth.host_db(n, base_seed=33)
+    q = synth.host_queries(nq, batch_id=33, planted_from=db, planted_ids=np.arange(0, n, max(1, n // 8))[:8])
+    h = _db(db)
+    s, i = h.search(q, k, qnorm=native.QNORM_L2, mode=native.MODE_TC)
+    t = h.timing()
+    assert t.last_mode == native.MODE_TC
+    xqn = orc.normalize_queries(torch.from_numpy(q)).numpy()
+    D, I = orc.knn_exact_blockwise(xqn, orc.db_iterator(db, 262144), k)
+    full = orc.all_scores_ip(xqn, db)
+    for r in range(nq):
+        orc.check_topk(s[r], i[r], D[r], I[r], full[r], tol=TOL, n_valid=min(n, k))
+    assert t.last_tc_fallbacks <= max(2, nq // 10), f"{t.last_tc_fallbacks} certificate fallbacks on iid data"
+    # AUTO must keep a large batch with a large k on the tensor-core path
+    h.search(synth.host_queries(512, 1, normalise=True), k)
+    assert h.timing().last_mode == native.MODE_TC
+    h.close()
+
+
 def test_tc_matches_gemv_path_bitwise_ids():
     n, nq, k = 50000, 64, 10
     db = synth.host_db(n, base_seed=41)
