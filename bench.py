@@ -286,13 +286,16 @@ def run_embed(args, steps=3, warmup=3, cpu_baseline=True):
     sm_mhz = clocks.get("sm_mhz") or 1965.0
     props = torch.cuda.get_device_properties(local_rank)
     if tc_mode:
-        # fp32-grade accuracy on the bf16 tensor pipe costs three MMAs per product (hi.hi + lo.hi + hi.lo)
+        # fp32-grade accuracy on the bf16 tensor pipe costs three MMAs per product (hi.hi + lo.hi + hi.lo): the roofline
+        # fraction is quoted on the ALGORITHMIC flops (2*514*256 per pair per layer); the MMA rate actually issued (3x) is
+        # reported beside it
         peaks = load_peaks()
-        achieved = 3.0 * fp32_equiv
-        roof = {"bound": "tensor", "achieved": achieved, "peak": peaks["tensor"], "unit": "TFLOP/s", "frac": achieved / peaks["tensor"],
+        roof = {"bound": "tensor", "achieved": fp32_equiv, "peak": peaks["tensor"], "unit": "TFLOP/s", "frac": fp32_equiv / peaks["tensor"],
                 "traffic": None, "kernel": "embed_edge_tc_kernel (both layers of one batch)",
-                "algorithmic": "3 bf16 MMAs (hi/lo split) x 2*514*256 flop per (i,j) pair per layer",
-                "fp32_equivalent_tflops": fp32_equiv, "peak_source": peaks["source"] + ", sustained bf16"}
+                "algorithmic": "2*514*256 flop per (i,j) pair per layer (fp32-grade result)",
+                "issued_mma_tflops": 3.0 * fp32_equiv, "issued_mma_frac": 3.0 * fp32_equiv / peaks["tensor"],
+                "peak_burst": peaks["tensor_burst"], "frac_burst": fp32_equiv / peaks["tensor_burst"],
+                "peak_source": peaks["source"] + ", sustained bf16"}
     else:
         peak = props.multi_processor_count * 128 * 2 * sm_mhz * 1e6 / 1e12
         roof = {"bound": "fp32", "achieved": fp32_equiv, "peak": peak, "unit": "TFLOP/s", "frac": fp32_equiv / peak, "traffic": None,
@@ -678,10 +681,16 @@ def run_gpu(args, wl, wl_name, steps=None, warmup=None):
     ms_total = e0.elapsed_time(e1)
     clocks = sampler.stop() if sampler else None
     if wl["mode"] == "tc":
-        # dominant-kernel time: event pairs around every GEMM+filter launch inside the library.  Read once, after the
-        # timed region, for its LAST search -- a search that ran under the sustained clocks of the loop (searches run
+        # dominant-kernel time: event pairs around every GEMM+filter launch inside the library (fcs_set_profiling; off in
+        # the timed region because events between kernels cost their programmatic-launch overlap).  A second back-to-back
+        # loop with the events on, read once for its LAST search -- a search that ran under sustained clocks (searches run
         # one at a time with host round trips in between boost higher and would flatter the roofline)
+        h.set_profiling(True)
+        for _ in range(max(3, min(args.steps, 10))):
+            step_device()
+        barrier()
         kernel_ms.append(h.timing().last_kernel_ms)
+        h.set_profiling(False)
     else:
         kernel_ms = [ms_total / args.steps]  # one kernel per step, launched back to back
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)

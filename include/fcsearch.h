@@ -159,9 +159,9 @@ int fcs_group_shard(fcs_group* g, int index, fcs_db** out); /* borrowed handle (
 int fcs_group_last_fallbacks(const fcs_group* g);           /* exact-scan fallbacks of the last search, all shards */
 int fcs_group_destroy(fcs_group* g);
 
-/* last_search_ms needs fcs_set_profiling(db, 1) (two event records per call; off by default because an event
- * between two scan kernels prevents their programmatic-dependent-launch overlap).  The TC path always times
- * its GEMM launches (last_kernel_ms). */
+/* last_search_ms and the tensor-core path's last_kernel_ms (event pairs around its GEMM+filter launches) need
+ * fcs_set_profiling(db, 1); off by default because an event between two kernels prevents their
+ * programmatic-dependent-launch overlap (scan after scan; GEMM round after selection). */
 int fcs_set_profiling(fcs_db* db, int enable);
 int fcs_get_timing(const fcs_db* db, fcs_timing* out);
 

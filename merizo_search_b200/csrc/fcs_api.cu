@@ -393,6 +393,7 @@ extern "C" int fcs_db_finalize(fcs_db* db) {
     if (db->flags & FCS_DB_KEEP_BF16) {
         int rc = tc_create(&db->tc, db->device, db->sm_count, db->rows, db->n_rows, uint32_t(db->id_offset), db->stream);
         if (rc != FCS_OK) return FCS_FAIL(rc, "fcs_db_finalize: tensor-core path setup failed: %s", tc_last_error());
+        tc_set_timing(db->tc, db->profiling);
     }
     db->finalized = true;
     return FCS_OK;
@@ -665,6 +666,7 @@ extern "C" int fcs_set_profiling(fcs_db* db, int enable) {
     if (!db) return FCS_FAIL(FCS_ERR_INVALID, "fcs_set_profiling: db is NULL");
     db->profiling = enable != 0;
     if (!db->profiling) db->ev_valid = false;
+    if (db->tc) tc_set_timing(db->tc, db->profiling);
     return FCS_OK;
 }
 

@@ -18,19 +18,22 @@
 //          512 columns; the epilogue of tile t drains its buffer while the MMAs of the other three run.
 //        * warps 5..20: epilogue, one THREAD PER QUERY (tcgen05.ld 32x32b: lane = accumulator row).
 //          Each thread reduces its scores 32 at a time with 3-input max, compares the group maximum
-//          with the query's threshold and only on a hit scans the 8-column sub-groups and appends
-//          (score,row) keys to the query's candidate buffer in HBM (slots reserved with one atomic).
+//          with the query's threshold and only on a hit re-reads the 8-column sub-group from TMEM and appends
+//          (score,row) keys to the query's candidate buffer in HBM (slots reserved with one atomic per 16).
 //
 //   The threshold is a per-query constant during a launch.  It comes from a SAMPLE of the database, not from a
 //   running top-k': the rows above the m-th best score of a sample of S rows number about m*N/S in the whole
 //   shard, so a small m and a large N/S give a good threshold after very little work.  A search is therefore
-//     round 0   32 tiles spread evenly over the shard (4096 rows), every score recorded (slot = sample row);
-//     round i   a larger, nested strided sample, threshold = rank-m_i score of what has been seen
-//               (m_i chosen so that about C1 = 1024 rows of the round qualify);
-//     sweep     every tile that was not sampled, threshold = rank-24 score of the last sample (about
-//               max(3k', 512) rows qualify) -- 95 % of the rows, at a hit density the epilogue absorbs;
-//   each followed by tc_select_kernel (one block per query, radix select on the order-preserving score word).
-//   Every tile is multiplied exactly once.  cfg3 (10 M rows) takes 3 GEMM launches instead of 9.
+//     round 0   8-32 tiles spread evenly over the shard (1024-4096 rows), every score recorded (slot = sample row);
+//     round i   a nested strided sample 8x the size of what has been seen, threshold = the rank-m_i score of that
+//               (m_i ~ 18: about 128 rows of the round qualify -- hits are what the epilogue pays for);
+//     sweep     every tile that was not sampled (~94 % of the rows), threshold = rank-24 score of the last sample:
+//               about max(2.4 k', 384) rows qualify, a hit density the epilogue absorbs;
+//   each followed by tc_select_kernel (one block per query, radix select on the order-preserving score word), and each
+//   GEMM round after the first launched programmatically behind its selection kernel (setup and operand prefetch overlap
+//   the selection's tail).  Every tile is multiplied exactly once.  cfg3 (10 M rows x 4096 queries) runs 5 GEMM launches:
+//   16 / 92 / 617 / 4158 tiles of samples (0.9 ms, 6 % of the rows) and a 73 k-tile sweep (7.3 ms) -- where round 1's
+//   geometric rounds (x3 rows per round at 2k' hits each) needed 9 launches and 2.8 ms for the first 2.2 M rows.
 //
 //   K4  tc_rescore_kernel -- one block (4 warps) per query.  Phase A: the k' best approximate candidates are gathered
 //        (fp32 rows), their inner products recomputed exactly, the k best kept; certificate
@@ -270,6 +273,8 @@ struct TcGemmParams {
     int first_round;       // round 0: thresholds are -inf, slot = idx * 128 + column, no atomics
     int trace_on;          // debug builds (FCS_TC_TRACE): record cycle stamps in this launch
     int res_block;         // slots reserved per atomic: small when many CTAs share a query group (unused slots are waste)
+    int pdl;               // launched with programmatic stream serialization behind a selection kernel (rounds >= 1): only
+                           // the epilogue depends on it (thresholds, candidate buffers); operands are immutable by then
 };
 
 __device__ __forceinline__ int64_t tile_of(const TcGemmParams& p, int64_t idx) {
@@ -434,6 +439,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_filter_kernel(const TcG
         const int quad = warp & 3;      // TMEM lane quadrant this warp may access
         const uint32_t lane_base = uint32_t(quad * 32) << 16;
         uint32_t it = 0;
+        // Everything the preceding selection kernel writes (thresholds, counters, compacted candidates) is touched by the
+        // epilogue only: with a programmatic launch the producer and the MMA issuers have been filling the pipeline while
+        // that kernel was finishing.
+        if (p.pdl) pdl_wait();
         for (int64_t s = s_begin; s < s_end;) {
             const int64_t qg = s / n_tiles, ti = s - qg * n_tiles;
             const int64_t seg_len = (s_end - s < n_tiles - ti) ? (s_end - s) : (n_tiles - ti);
@@ -606,6 +615,7 @@ __global__ void __launch_bounds__(SEL_NT) tc_select_kernel(const TcSelectParams 
     __shared__ uint32_t s_part[3][SEL_NT / 32];
     __shared__ int s_misc[4];  // [0] digit, [1] remaining rank, [2] survivors written, [3] others written
     const int q = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    pdl_launch_dependents();  // the next round's GEMM may set up and prefetch while the last blocks of this kernel run
     unsigned raw = p.cnt[q];
     if (raw > unsigned(p.cap)) {  // candidates were lost: the query goes to the exact scan in the end
         if (tid == 0) atomicOr(p.flags + q, 1u);
@@ -1052,10 +1062,13 @@ struct TcState {
     cudaEvent_t ev_done = nullptr;
     int last_rounds = 0;
     bool last_valid = false;
+    bool last_timed = false;
     // FCS_TC_PHASES=1: an event in front of every kernel of a search, printed by tc_last_kernel_ms (diagnostics)
     bool phases = false;
     int r0_tiles = TC_R0_TILES;
     bool r0_auto = true;
+    bool pdl_on = true;      // FCS_TC_PDL=0 turns the programmatic launches off (A/B)
+    bool timing_on = false;  // event pairs around the GEMM launches (fcs_set_profiling): they cost the PDL overlap
     std::vector<cudaEvent_t> pev;
     std::vector<std::string> plabel;
     int n_pev = 0;
@@ -1090,11 +1103,13 @@ static std::vector<TcRound> tc_plan(const TcState* s, int kp, int n_qgroups) {
     if (t_last < t0) t_last = t0;
     const int64_t stride = nt / t_last;  // >= 2
     auto clamp_rank = [](double r) { return int(r < 1.0 ? 1.0 : (r > double(TC_MAX_RANK) ? double(TC_MAX_RANK) : std::ceil(r))); };
+    // hits cost more than launches even for small batches (512 queries: 5 rounds of 128 hits beat 4 rounds of 512 hits)
+    const double c_sample = s->c_sample;
     // nested samples t0 < T_1 < ... < t_last, each at most c_sample/m_min times the previous
     std::vector<int64_t> ts{t0};
     if (t_last > t0) {
         const double ratio = double(t_last) / double(t0);
-        int ns = int(std::ceil(std::log(ratio) / std::log(s->c_sample / s->m_min) - 1e-9));
+        int ns = int(std::ceil(std::log(ratio) / std::log(c_sample / s->m_min) - 1e-9));
         if (ns < 1) ns = 1;
         for (int i = 1; i <= ns; ++i) {
             int64_t t = (i == ns) ? t_last : int64_t(std::llround(double(t0) * std::pow(ratio, double(i) / ns)));
@@ -1111,7 +1126,7 @@ static std::vector<TcRound> tc_plan(const TcState* s, int kp, int n_qgroups) {
         r.first = i == 0 ? 1 : 0;
         const double seen = double(ts[i]);
         const double next = (i + 1 < ts.size()) ? double(ts[i + 1] - ts[i]) : double(nt - ts[i]);
-        const double target = (i + 1 < ts.size()) ? s->c_sample : cf;
+        const double target = (i + 1 < ts.size()) ? c_sample : cf;
         r.rank = clamp_rank(target * seen / next);
         plan.push_back(r);
     }
@@ -1135,8 +1150,12 @@ int tc_max_k() { return FCS_MAX_K; }
 int tc_last_rounds(const TcState* s) { return s ? s->last_rounds : 0; }
 uint64_t tc_image_bytes(const TcState* s) { return s ? uint64_t(s->n_tiles) * B_TILE_BYTES : 0; }
 
+void tc_set_timing(TcState* s, bool on) {
+    if (s) s->timing_on = on;
+}
+
 float tc_last_kernel_ms(TcState* s) {
-    if (!s || !s->last_valid) return 0.f;
+    if (!s || !s->last_valid || !s->last_timed) return 0.f;
     if (cudaEventSynchronize(s->ev_done) != cudaSuccess) return 0.f;
     float total = 0.f;
     if (s->phases) {
@@ -1200,6 +1219,7 @@ int tc_create(TcState** out, int device, int sm_count, const float* rows, int64_
     s->m_min = env_double("FCS_TC_M_MIN", s->m_min, 1.0, 64.0);
     s->r0_tiles = int(env_double("FCS_TC_R0_TILES", TC_R0_TILES, 1.0, TC_R0_TILES));
     s->r0_auto = getenv("FCS_TC_R0_TILES") == nullptr;
+    if (const char* e = getenv("FCS_TC_PDL")) s->pdl_on = atoi(e) != 0;
     s->phases = getenv("FCS_TC_PHASES") != nullptr;
     auto run = [&]() -> int {
         TC_CUDA(cudaFuncSetAttribute(tc_gemm_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
@@ -1294,7 +1314,7 @@ static void tc_launch_prep(TcState* s, const float* q_dev, int nq, int nq_pad, i
     tc_prep_kernel<<<(nq_pad + 3) / 4, 128, 0, stream>>>(pp);
 }
 
-static void tc_launch_gemm(TcState* s, const TcRound& r, int nq, int n_qgroups, int cap, cudaStream_t stream, int trace_on) {
+static void tc_launch_gemm(TcState* s, const TcRound& r, int nq, int n_qgroups, int cap, cudaStream_t stream, int trace_on, bool pdl) {
     TcGemmParams gp = {};
     gp.a_img = s->a_img; gp.b_img = s->b_img; gp.n_rows = s->n_rows; gp.nq = nq; gp.n_qgroups = n_qgroups;
     gp.n_idx = r.n_idx; gp.j0 = r.j0; gp.stride = r.stride; gp.comp_T = r.comp_T;
@@ -1306,7 +1326,22 @@ static void tc_launch_gemm(TcState* s, const TcRound& r, int nq, int n_qgroups, 
     const int segs = (grid + n_qgroups - 1) / n_qgroups + 1;
     const int rb = 512 / segs;
     gp.res_block = rb < 2 ? 2 : (rb > TC_RES_MAX ? TC_RES_MAX : rb);
-    tc_gemm_filter_kernel<<<grid, TC_THREADS, TC_SMEM, stream>>>(gp);
+    gp.pdl = pdl ? 1 : 0;
+    if (!pdl) {
+        tc_gemm_filter_kernel<<<grid, TC_THREADS, TC_SMEM, stream>>>(gp);
+        return;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = TC_SMEM;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    (void)cudaLaunchKernelEx(&cfg, tc_gemm_filter_kernel, gp);
 }
 
 // Enqueues the whole batched search on `stream` and returns without synchronising.  Queries whose certificate failed
@@ -1344,10 +1379,12 @@ int tc_search(TcState* s, const float* q_dev, int nq, int k, int kprime, int qno
     static const int trace_round = getenv("FCS_TC_TRACE_ROUND") ? atoi(getenv("FCS_TC_TRACE_ROUND")) : -1;
     int rounds = 0;
     for (const TcRound& r : plan) {
-        const bool timed = rounds < TcState::MAX_ROUNDS;
+        const bool timed = s->timing_on && rounds < TcState::MAX_ROUNDS;
         tc_phase(s, r.first ? "gemm-dump" : (r.comp_T ? "gemm-sweep" : "gemm-sample"), stream);
         if (timed) TC_CUDA(cudaEventRecord(s->ev[2 * rounds], stream));
-        tc_launch_gemm(s, r, nq, n_qgroups, cap, stream, trace_round == rounds ? 1 : 0);
+        // rounds >= 1 follow a selection kernel and overlap its tail (programmatic dependent launch) -- unless events are
+        // recorded in between (profiling, phase diagnostics), which serialises the two kernels again
+        tc_launch_gemm(s, r, nq, n_qgroups, cap, stream, trace_round == rounds ? 1 : 0, rounds > 0 && s->pdl_on && !s->timing_on && !s->phases);
         TC_CUDA(cudaGetLastError());
         if (timed) TC_CUDA(cudaEventRecord(s->ev[2 * rounds + 1], stream));
         tc_phase(s, "select", stream);
@@ -1378,6 +1415,7 @@ int tc_search(TcState* s, const float* q_dev, int nq, int k, int kprime, int qno
     TC_CUDA(cudaEventRecord(s->ev_done, stream));
     s->last_rounds = rounds;
     s->last_valid = true;
+    s->last_timed = s->timing_on;
     fbq->count_dev = s->n_flagged;
     fbq->list_dev = s->fb_list;
     fbq->q_dev = s->fb_q;
@@ -1439,7 +1477,7 @@ int tc_debug_approx(TcState* s, const float* q_dev, int nq, int qnorm, float* ou
     tc_launch_prep(s, q_dev, nq, nq_pad, qnorm, unsigned(s->n_tiles * TC_N), stream);
     TC_CUDA(cudaGetLastError());
     const TcRound r0 = {s->n_tiles, 0, 1, 0, 1, 1, 0};
-    tc_launch_gemm(s, r0, nq, n_qgroups, TC_CAP, stream, 0);
+    tc_launch_gemm(s, r0, nq, n_qgroups, TC_CAP, stream, 0, false);
     TC_CUDA(cudaGetLastError());
     TC_CUDA(cudaStreamSynchronize(stream));
     std::string keys(size_t(nq) * TC_CAP * 8, '\0');

@@ -20,7 +20,8 @@ int tc_create(TcState** out, int device, int sm_count, const float* rows, int64_
               cudaStream_t stream);
 uint64_t tc_image_bytes(const TcState* s);
 // The next three wait for the last search's device work (an event), then read what it recorded.
-float tc_last_kernel_ms(TcState* s);  // sum over the GEMM+filter launches of the last search
+void tc_set_timing(TcState* s, bool on);  // event pairs around the GEMM+filter launches of every search (off by default)
+float tc_last_kernel_ms(TcState* s);  // sum over the GEMM+filter launches of the last search (0 unless timing was on)
 int tc_last_flagged(TcState* s);      // length of the last search's fallback queue
 int tc_last_rounds(const TcState* s);
 void tc_destroy(TcState* s);
