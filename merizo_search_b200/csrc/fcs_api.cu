@@ -500,16 +500,17 @@ int fcs::api_finish_pending(fcs_db* db, cudaStream_t stream, int* n_queued) {
     return FCS_OK;
 }
 
-// AUTO: the batched tensor-core path pays a fixed ~0.15 ms (three GEMM rounds on samples, selection launches) and then
-// ~256 flop per (query,row) at ~1.2 PFLOP/s; the exact scan streams 512 B per row once per 8 queries at ~6.5 TB/s
-// with ~10 us per launch.  Pick the cheaper estimate.
+// AUTO picks the cheaper of two fitted cost models (profiles/r02_auto_model.json: 5 shard sizes x 10 batch sizes on B200,
+// no wrong choice on that grid):
+//   exact scan    ceil(nq/8) * ceil(k/128) passes, each 50 us + 82 ns per 1000 rows (8 queries per pass: issue-bound FFMA2);
+//   tensor cores  125 us of sampling rounds / selections / rescore + 100 ns per 1000 rows per 512-query group.
+// One scan pass (nq <= 8) always wins; with the coverage mask on only the scan applies.
 bool fcs::api_auto_prefers_tc(const fcs_db* db, int nq, int k, bool mask_on) {
     if (!db->tc || mask_on || k > tc_max_k() || nq < tc_min_batch()) return false;
     const double rows = double(db->n_rows);
-    const double groups = double((nq + GEMV_MAX_NQ - 1) / GEMV_MAX_NQ);
-    const double t_gemv = groups * (1.0e-5 + rows * 512.0 / 6.5e12 * 1.35);
-    const double nq_pad = double((nq + 511) / 512 * 512);
-    const double t_tc = 1.5e-4 + rows * 256.0 / 5.0e12 + nq_pad * rows * 256.0 / 1.2e15;
+    const double passes = double((nq + GEMV_MAX_NQ - 1) / GEMV_MAX_NQ) * double((k + GEMV_MAX_K - 1) / GEMV_MAX_K);
+    const double t_gemv = passes * (5.0e-5 + rows * 8.2e-11);
+    const double t_tc = 1.25e-4 + double((nq + 511) / 512) * rows * 1.0e-10;
     return t_tc < t_gemv;
 }
 

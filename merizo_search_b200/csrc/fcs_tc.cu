@@ -1145,7 +1145,7 @@ void tc_phase_mark(TcState* s, const char* label, cudaStream_t stream) {
 }
 
 const char* tc_last_error() { return g_tc_error.c_str(); }
-int tc_min_batch() { return 32; }
+int tc_min_batch() { return GEMV_MAX_NQ + 1; }  // one exact-scan pass always wins
 int tc_max_k() { return FCS_MAX_K; }
 int tc_last_rounds(const TcState* s) { return s ? s->last_rounds : 0; }
 uint64_t tc_image_bytes(const TcState* s) { return s ? uint64_t(s->n_tiles) * B_TILE_BYTES : 0; }

@@ -23,7 +23,7 @@ from typing import Dict, Iterable, Optional, Tuple
 
 import numpy as np
 
-from . import dbindex, native
+from . import dbindex, native, serve
 from .engine import LocalEngine
 
 logger = logging.getLogger(__name__)
@@ -118,6 +118,11 @@ def read_database(db_name: str, device):
         target_index, lengths = dbindex.load_index(db_name)
         resident = _resident_get(key, pt_path)
         if resident is None:
+            remote = serve.connect(pt_path, "pt")  # FCS_SERVER: a resident copy in another process (serve.py)
+            if remote is not None:
+                resident = ResidentDatabase(remote, "pt")
+                _resident_put(key, resident, pt_path)
+        if resident is None:
             target_db = torch.load(db_name + ".pt", map_location="cpu")
             rows = target_db.detach().to(torch.float32).contiguous().numpy()
             assert len(target_index) == rows.shape[0]
@@ -188,6 +193,11 @@ def load_resident_file(path: str, n_rows: int, device=None) -> ResidentDatabase:
         return resident
     if os.path.getsize(path) < n_rows * DIM * 4:
         raise native.FcsError(native.ERR_INVALID, f"{path}: {os.path.getsize(path)} bytes cannot hold {n_rows} x {DIM} fp32 rows")
+    remote = serve.connect(path, "faiss")  # FCS_SERVER: a resident copy in another process (serve.py)
+    if remote is not None:
+        resident = ResidentDatabase(remote, "faiss")
+        _resident_put(key, resident, path)
+        return resident
     t0 = time.time()
     eng = LocalEngine(n_rows, devices=_devices(device), normalise_rows=False, keep_bf16=_want_bf16(), has_lengths=False)
     eng.upload_file(path)

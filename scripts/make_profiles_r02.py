@@ -1,0 +1,86 @@
+"""Turn the raw ncu exports of scripts/r2_evidence.sh (gpurun_out/) into the tracked evidence files under profiles/:
+    python scripts/make_profiles_r02.py
+"""
+import collections
+import csv
+import json
+import os
+import subprocess
+
+G, P = "gpurun_out", "profiles"
+
+
+def rows(path):
+    return [r for r in csv.reader(open(path)) if len(r) > 10]
+
+
+def per_launch(path):
+    R = rows(path)
+    hdr = R[0]
+    mi, vi, ii, ki = hdr.index("Metric Name"), hdr.index("Metric Value"), hdr.index("ID"), hdr.index("Kernel Name")
+    d = collections.OrderedDict()
+    for r in R[1:]:
+        e = d.setdefault(r[ii], {"kernel": r[ki].split("(")[0].replace("fcs::<unnamed>::", "").replace("void ", "")})
+        try:
+            e[r[mi]] = float(r[vi].replace(",", ""))
+        except ValueError:
+            e[r[mi]] = None
+    return list(d.values())
+
+
+# 1. launch list of one cfg3 search (serialised by ncu: compare shares, not absolutes)
+L = per_launch(os.path.join(G, "r02_launches_cfg3_raw.csv"))
+last = max(i for i, e in enumerate(L) if "tc_prep" in e["kernel"])
+search = L[last:last + 17]
+with open(os.path.join(P, "r02_launches_cfg3.csv"), "w") as fh:
+    fh.write("# one cfg3 search (10 M rows x 4096 queries, k=100), ncu --metrics gpu__time_duration.sum --clock-control none; kernels in launch order\n")
+    fh.write("kernel,duration_us\n")
+    for e in search:
+        fh.write("%s,%.1f\n" % (e["kernel"], e["gpu__time_duration.sum"] / 1e3))
+tot = sum(e["gpu__time_duration.sum"] for e in search)
+share = collections.OrderedDict()
+for e in search:
+    share[e["kernel"]] = share.get(e["kernel"], 0.0) + e["gpu__time_duration.sum"]
+print("cfg3 search: %.1f us over %d launches" % (tot / 1e3, len(search)))
+for k, v in share.items():
+    print("  %-34s %9.1f us  %5.1f %%" % (k, v / 1e3, 100 * v / tot))
+
+# 2. K3 rounds: DRAM traffic, L2 hit rate, tensor instructions
+R = per_launch(os.path.join(G, "r02_k3_rounds_raw.csv"))
+per_round = []
+for i, e in enumerate(R):
+    per_round.append({"round": i, "us": e["gpu__time_duration.sum"] / 1e3, "dram_read": e["dram__bytes_read.sum"], "dram_write": e["dram__bytes_write.sum"],
+                      "l2_hit_pct": e.get("lts__t_sector_hit_rate.pct"), "tensor_instructions": e.get("sm__inst_executed_pipe_tensor.sum")})
+rd, wr = sum(r["dram_read"] for r in per_round), sum(r["dram_write"] for r in per_round)
+json.dump({"kernel": "tc_gemm_filter_kernel (%d rounds of one cfg3 search)" % len(per_round), "workload": "cfg3 (10M rows x 4096 queries, k=100)",
+           "dram_bytes_per_launch": rd + wr, "dram_bytes_read": rd, "dram_bytes_write": wr, "algorithmic_bytes": 10_000_000 * 256,
+           "captured": "round 2, ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum over the GEMM+filter launches of one search (scripts/r2_evidence.sh)",
+           "note": "sum over the GEMM+filter launches of one search (the roofline 'achieved' is also per search); the bf16 operand images are 2.56 GB "
+                   "and are streamed once per 512-query group (8 groups = 20.5 GB requested from L2)",
+           "per_round": per_round}, open(os.path.join(P, "traffic_cfg3.json"), "w"), indent=1)
+print("K3 DRAM traffic per search: %.2f GB (%.2fx the 2.56 GB image)" % ((rd + wr) / 1e9, (rd + wr) / 2.56e9))
+
+# 3. K2 traffic
+for wl, rows_, desc in (("cfg2", 500_000, "500000 rows x 514 B, 1 query, k=10"), ("cfg4", 45_625_000, "45.625 M rows x 512 B, 1 query, k=10")):
+    K = per_launch(os.path.join(G, f"r02_k2_{wl}_raw.csv"))
+    e = K[-1]
+    alg = rows_ * (514 if wl == "cfg2" else 512)
+    json.dump({"kernel": e["kernel"], "workload": f"{wl} ({desc})", "dram_bytes_per_launch": e["dram__bytes_read.sum"] + e["dram__bytes_write.sum"],
+               "dram_bytes_read": e["dram__bytes_read.sum"], "dram_bytes_write": e["dram__bytes_write.sum"], "algorithmic_bytes": alg,
+               "duration_us_under_ncu": e["gpu__time_duration.sum"] / 1e3,
+               "captured": "round 2, ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum, one launch (scripts/r2_evidence.sh)"},
+              open(os.path.join(P, f"traffic_{wl}.json"), "w"), indent=1)
+    print(wl, "dram %.4f GB vs algorithmic %.4f GB" % ((e["dram__bytes_read.sum"] + e["dram__bytes_write.sum"]) / 1e9, alg / 1e9))
+
+# 4. --set full of the sweep: raw page as CSV (metric, unit, value)
+rep = os.path.join(G, "r02_prof_k3_sweep.ncu-rep")
+if os.path.exists(rep):
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    R = list(csv.reader(raw.splitlines()))
+    hdr, units, vals = R[0], R[1], R[2]
+    with open(os.path.join(P, "r02_ncu_k3_sweep_raw.csv"), "w") as fh:
+        fh.write("# ncu --set full --clock-control none of the sweep round of one cfg3 search (tc_gemm_filter_kernel, 73 k tiles x 8 query groups)\n")
+        fh.write("metric,unit,value\n")
+        for h, u, v in zip(hdr, units, vals):
+            fh.write('"%s","%s","%s"\n' % (h, u, v))
+    print("sweep raw page:", len(hdr), "metrics")

@@ -94,3 +94,32 @@ def test_dbsearch_faiss_driver_skip_tmalign(tiny_faiss_db, tmp_path):
         assert h["query"] == f"query{[4, 17, 33][q]}" and h["tmalign_output"] is None and h["dom_str"] == "1-10"
     assert results[0][0]["dbindex"] == 4 and results[1][0]["dbindex"] == 17 and results[2][0]["dbindex"] == 33
     b200.release_all()
+
+
+def test_residency_server_keeps_the_pt_database_across_clients(pt_db, tmp_path, monkeypatch):
+    """serve.py: a server process-alike holds the database in HBM; a client's read_database finds it
+    through FCS_SERVER and its searches give the reference's answer without loading the matrix."""
+    import threading
+
+    from merizo_search_b200 import serve
+
+    base, rows, lens, index = pt_db
+    eng, info = serve._load(base, [0])
+    sock = str(tmp_path / "fcs.sock")
+    ready = threading.Event()
+    th = threading.Thread(target=serve.serve, args=(eng, sock, info, ready), daemon=True)
+    th.start()
+    assert ready.wait(10)
+    monkeypatch.setenv("FCS_SERVER", sock)
+    b200.release_all()
+    target = b200.read_database(base, torch.device("cuda"))
+    assert isinstance(target["database"].engine, serve.RemoteEngine) and target["database"].size(0) == len(index)
+    dbt, lt = torch.from_numpy(rows), torch.from_numpy(lens.astype(np.float32))
+    emb = torch.from_numpy(synth.host_queries(1, 61))
+    res = b200.search_query_against_db({"embedding": emb, "seq": "G" * 150}, target, 0.7, 10)
+    ws, wi, full = orc.search_torch_flavour(dbt, lt, emb[0], 150, 0.7, 10)
+    orc.check_topk(res["scores"].numpy(), res["indices"].numpy(), ws.numpy(), wi.numpy(), full.numpy(), tol=1e-5)
+    target["database"].engine.shutdown_server()
+    th.join(10)
+    b200.release_all()
+    eng.close()

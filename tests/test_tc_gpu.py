@@ -130,7 +130,12 @@ def test_auto_mode_picks_paths():
     h.search(synth.host_queries(512, 1, normalise=True), 5)
     assert h.timing().last_mode == native.MODE_TC
     h.close()
-    small = _db(synth.host_db(3000, base_seed=72))
-    small.search(synth.host_queries(64, 1, normalise=True), 5)  # 8 scan launches beat the TC path's fixed cost
-    assert small.timing().last_mode == native.MODE_GEMV
-    small.close()
+    h = _db(db)
+    h.search(synth.host_queries(8, 1, normalise=True), 5)  # one scan pass always beats the TC path's fixed cost
+    assert h.timing().last_mode == native.MODE_GEMV
+    h.search(synth.host_queries(16, 1, normalise=True), 5)  # two passes over 300 k rows vs 125 us + one sweep: scan still wins
+    assert h.timing().last_mode == native.MODE_GEMV
+    h.search(synth.host_queries(64, 1, normalise=True), 5)
+    assert h.timing().last_mode == native.MODE_TC
+    h.search(synth.host_queries(64, 1, normalise=True), 5, qlen=None)
+    h.close()
