@@ -704,9 +704,11 @@ def run_gpu(args, wl, wl_name, steps=None, warmup=None):
     # ---- e2e: host buffers through the public API (H2D + D2H inside the timed region).
     # 1 GPU: native.Database.search (fcs_search).  N GPUs: engine.DistributedEngine.search_host (pinned host
     # queries -> H2D -> shard search -> NCCL all-gather of keys -> GPU merge -> D2H) on every rank.
+    e2e_out = (np.empty((nq, k), dtype=np.float32), np.empty((nq, k), dtype=np.int64))  # a batch loop reuses its result arrays
+
     def step_e2e():
         if world == 1:
-            return h.search(q_host.numpy(), k, qlen=qlen, mincov=mincov, mode=mode)
+            return h.search(q_host.numpy(), k, qlen=qlen, mincov=mincov, mode=mode, out=e2e_out)
         with torch.cuda.stream(stream):
             out_ = deng.search_host(q_host, k, qlen=qlen, mincov=mincov, mode=mode)
         return out_

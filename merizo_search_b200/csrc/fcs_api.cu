@@ -198,6 +198,7 @@ extern "C" int fcs_db_create(int device, int64_t n_rows, int dim, int64_t id_off
         FCS_CUDA(cudaStreamCreateWithFlags(&db->stream, cudaStreamNonBlocking));
         FCS_CUDA(cudaEventCreate(&db->ev0));
         FCS_CUDA(cudaEventCreate(&db->ev1));
+        FCS_CUDA(cudaEventCreateWithFlags(&db->out_ev, cudaEventDisableTiming));
         FCS_CUDA(cudaMalloc(&db->rows, size_t(n_rows) * ROW_BYTES));
         if (flags & FCS_DB_HAS_LENGTHS) FCS_CUDA(cudaMalloc(&db->lens, size_t(n_rows) * sizeof(uint16_t)));
         FCS_CUDA(cudaMalloc(&db->gemv_scratch, gemv_scratch_bytes(db->sm_count)));
@@ -243,6 +244,7 @@ extern "C" int fcs_db_destroy(fcs_db* db) {
     }
     if (db->ev0) cudaEventDestroy(db->ev0);
     if (db->ev1) cudaEventDestroy(db->ev1);
+    if (db->out_ev) cudaEventDestroy(db->out_ev);
     if (db->stream) cudaStreamDestroy(db->stream);
     (void)cudaGetLastError();
     delete db;
@@ -617,7 +619,11 @@ extern "C" int fcs_search(fcs_db* db, const float* q, int nq, const int32_t* qle
         if (rc != FCS_OK) return rc;
         for (int attempt = 0; attempt < 2; ++attempt) {
             FCS_CUDA(cudaMemcpyAsync(db->h_scores, db->d_scores, entries * sizeof(float), cudaMemcpyDeviceToHost, db->stream));
+            FCS_CUDA(cudaEventRecord(db->out_ev, db->stream));
             FCS_CUDA(cudaMemcpyAsync(db->h_ids, db->d_ids, entries * sizeof(int64_t), cudaMemcpyDeviceToHost, db->stream));
+            // the scores go to the caller's buffer while the (twice as large) ids are still crossing PCIe
+            FCS_CUDA(cudaEventSynchronize(db->out_ev));
+            memcpy(out_scores, db->h_scores, entries * sizeof(float));
             FCS_CUDA(cudaStreamSynchronize(db->stream));
             // a fallback queue longer than the passes enqueued behind the search: scan the rest, copy again
             int queued = 0;
@@ -625,6 +631,8 @@ extern "C" int fcs_search(fcs_db* db, const float* q, int nq, const int32_t* qle
             if ((rc = api_finish_pending(db, db->stream, &queued)) != FCS_OK) return rc;
             if (!had_pending || queued <= FB_ASYNC_PASSES * GEMV_MAX_NQ) break;
         }
+        memcpy(out_ids, db->h_ids, entries * sizeof(int64_t));
+        return FCS_OK;
     }
     memcpy(out_scores, db->h_scores, entries * sizeof(float));
     memcpy(out_ids, db->h_ids, entries * sizeof(int64_t));

@@ -53,6 +53,7 @@ struct fcs_db {
 
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t out_ev = nullptr;  // fcs_search: scores have arrived on the host (their copy to the caller overlaps the ids' D2H)
     bool ev_valid = false;
     bool profiling = false;  // record ev0/ev1 around every search (off: event records between two scan kernels
                              // would break their programmatic-dependent-launch overlap)

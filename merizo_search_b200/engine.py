@@ -147,9 +147,9 @@ class LocalEngine:
 
     # -- search ------------------------------------------------------------------------------
     def search(self, q: np.ndarray, k: int, qlen: Optional[np.ndarray] = None, mincov: float = 0.0,
-               qnorm: int = native.QNORM_NONE, mode: int = native.MODE_AUTO, kprime: int = 0):
-        """(scores f32 [nq,k], ids i64 [nq,k]) as host arrays; exact; global ids."""
-        return self.group.search(q, k, qlen=qlen, mincov=mincov, qnorm=qnorm, mode=mode, kprime=kprime)
+               qnorm: int = native.QNORM_NONE, mode: int = native.MODE_AUTO, kprime: int = 0, out=None):
+        """(scores f32 [nq,k], ids i64 [nq,k]) as host arrays; exact; global ids.  `out=(scores, ids)` reuses the caller's arrays."""
+        return self.group.search(q, k, qlen=qlen, mincov=mincov, qnorm=qnorm, mode=mode, kprime=kprime, out=out)
 
     def close(self) -> None:
         self.group.close()

@@ -145,6 +145,17 @@ def _np_ptr(a: Optional[np.ndarray]):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
+def _out_arrays(out, nq: int, k: int):
+    """Result arrays of a host-buffer search: fresh ones, or the caller's `out=(scores, ids)` after a shape/dtype check."""
+    if out is None:
+        return np.empty((nq, k), dtype=np.float32), np.empty((nq, k), dtype=np.int64)
+    scores, ids = out
+    if (scores.shape != (nq, k) or ids.shape != (nq, k) or scores.dtype != np.float32 or ids.dtype != np.int64
+            or not scores.flags.c_contiguous or not ids.flags.c_contiguous):
+        raise FcsError(ERR_INVALID, f"out must be C-contiguous (float32 [{nq},{k}], int64 [{nq},{k}])")
+    return scores, ids
+
+
 class Database:
     """One device-resident row shard (fcs_db).  Not re-entrant; do not share across forks."""
 
@@ -181,15 +192,15 @@ class Database:
 
     # -- search ----------------------------------------------------------------------------
     def search(self, q: np.ndarray, k: int, qlen: Optional[np.ndarray] = None, mincov: float = 0.0,
-               qnorm: int = QNORM_NONE, mode: int = MODE_AUTO, kprime: int = 0):
-        """Host buffers in, host buffers out: (scores f32 [nq,k], ids i64 [nq,k])."""
+               qnorm: int = QNORM_NONE, mode: int = MODE_AUTO, kprime: int = 0, out=None):
+        """Host buffers in, host buffers out: (scores f32 [nq,k], ids i64 [nq,k]).  `out=(scores, ids)` reuses the caller's
+        arrays (a loop that searches batch after batch avoids faulting in fresh result pages every call)."""
         q = np.ascontiguousarray(q, dtype=np.float32).reshape(-1, DIM)
         nq = q.shape[0]
         ql = None if qlen is None else np.ascontiguousarray(qlen, dtype=np.int32).reshape(-1)
         if ql is not None and ql.shape[0] != nq:
             raise FcsError(ERR_INVALID, "qlen must have one entry per query")
-        scores = np.empty((nq, int(k)), dtype=np.float32)
-        ids = np.empty((nq, int(k)), dtype=np.int64)
+        scores, ids = _out_arrays(out, nq, int(k))
         _check(self._lib.fcs_search(self._h, _np_ptr(q), nq, _np_ptr(ql), float(mincov), int(k), int(qnorm), int(mode),
                                     int(kprime), _np_ptr(scores), _np_ptr(ids)))
         return scores, ids
@@ -300,14 +311,13 @@ class Group:
         _check(self._lib.fcs_group_finalize(self._h))
 
     def search(self, q: np.ndarray, k: int, qlen: Optional[np.ndarray] = None, mincov: float = 0.0,
-               qnorm: int = QNORM_NONE, mode: int = MODE_AUTO, kprime: int = 0):
+               qnorm: int = QNORM_NONE, mode: int = MODE_AUTO, kprime: int = 0, out=None):
         q = np.ascontiguousarray(q, dtype=np.float32).reshape(-1, DIM)
         nq = q.shape[0]
         ql = None if qlen is None else np.ascontiguousarray(qlen, dtype=np.int32).reshape(-1)
         if ql is not None and ql.shape[0] != nq:
             raise FcsError(ERR_INVALID, "qlen must have one entry per query")
-        scores = np.empty((nq, int(k)), dtype=np.float32)
-        ids = np.empty((nq, int(k)), dtype=np.int64)
+        scores, ids = _out_arrays(out, nq, int(k))
         _check(self._lib.fcs_group_search(self._h, _np_ptr(q), nq, _np_ptr(ql), float(mincov), int(k), int(qnorm), int(mode),
                                           int(kprime), _np_ptr(scores), _np_ptr(ids)))
         return scores, ids
