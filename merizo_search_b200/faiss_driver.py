@@ -67,13 +67,45 @@ class RecordFiles:
         return self._cache[index_key]
 
     def names(self, ids: np.ndarray) -> List[str]:
-        """33-byte records: id left-justified, space padded, newline (dbutil.py:41-43, 107-108)."""
-        return [x.decode().rstrip() for x in self._names[np.asarray(ids, dtype=np.int64)]]
+        """33-byte records: id left-justified, space padded, newline (dbutil.py:41-43, 107-108).  One fancy-indexed read of
+        the record table, one vectorised decode + strip (no per-hit Python work)."""
+        recs = np.asarray(self._names[np.asarray(ids, dtype=np.int64)])
+        return np.char.rstrip(np.char.decode(recs, "ascii")).tolist()
 
-    def _ranges(self, index_key: str, data_key: str, ids: np.ndarray):
+    def _spans(self, index_key: str, data_key: str, ids: np.ndarray):
         idx, dat = self._pair(index_key, data_key)
         se = np.asarray(idx[np.asarray(ids, dtype=np.int64)])  # one fancy-indexed read for all hits
-        return [dat[int(s):int(e)] for s, e in se]
+        return se[:, 0], se[:, 1], dat
+
+    def _gather_bytes(self, index_key: str, data_key: str, ids: np.ndarray, chunk_bytes: int = 64 << 20):
+        """Payload bytes of every hit, concatenated: (buffer: bytes, offsets: int64 [n+1]).  The variable-length records are
+        gathered with ONE fancy-indexed read per chunk of hits (flat byte index = repeat(start) + position inside the
+        record), not one seek/read per hit (dbutil.py:131-145 retrieve_bytes)."""
+        starts, ends, dat = self._spans(index_key, data_key, ids)
+        lens = (ends - starts).astype(np.int64)
+        offs = np.zeros(len(lens) + 1, dtype=np.int64)
+        np.cumsum(lens, out=offs[1:])
+        parts = []
+        i0 = 0
+        while i0 < len(lens):
+            i1 = int(np.searchsorted(offs, offs[i0] + chunk_bytes, side="right")) - 1
+            i1 = max(i1, i0 + 1)
+            n_b = int(offs[i1] - offs[i0])
+            if n_b:
+                flat = np.repeat(starts[i0:i1] - (offs[i0:i1] - offs[i0]), lens[i0:i1]) + np.arange(n_b, dtype=np.int64)
+                parts.append(np.asarray(dat[flat]).tobytes())
+            i0 = i1
+        return b"".join(parts), offs
+
+    def _ranges(self, index_key: str, data_key: str, ids: np.ndarray):
+        buf, offs = self._gather_bytes(index_key, data_key, ids)
+        return [buf[int(a):int(b)] for a, b in zip(offs[:-1], offs[1:])]
+
+    def _strings(self, index_key: str, data_key: str, ids: np.ndarray) -> List[str]:
+        buf, offs = self._gather_bytes(index_key, data_key, ids)
+        text = buf.decode("ascii")  # ASCII: byte offsets are character offsets
+        o = offs.tolist()
+        return [text[o[i]:o[i + 1]] for i in range(len(o) - 1)]
 
     def lengths(self, ids) -> np.ndarray:
         """Domain lengths of the hits straight from the (start,end) table: no payload bytes are touched."""
@@ -82,12 +114,12 @@ class RecordFiles:
         return (se[:, 1] - se[:, 0]).astype(np.int64)
 
     def sequences(self, ids) -> List[str]:
-        return [bytes(b).decode("ascii") for b in self._ranges("sif", "sdf", ids)]
+        return self._strings("sif", "sdf", ids)
 
     def coords(self, ids) -> List[np.ndarray]:
         out = []
         for b in self._ranges("cif", "cdf", ids):
-            d = np.frombuffer(bytes(b), dtype=np.float32)
+            d = np.frombuffer(b, dtype=np.float32)
             assert d.size % 3 == 0
             out.append(d.reshape(-1, 3))
         return out
@@ -96,7 +128,7 @@ class RecordFiles:
         return "mdf" in self.info and "mif" in self.info
 
     def metadata(self, ids) -> List[str]:
-        return [bytes(b).decode("ascii") for b in self._ranges("mif", "mdf", ids)]
+        return self._strings("mif", "mdf", ids)
 
 
 def threshold_hits(D: np.ndarray, I: np.ndarray, mincos: float):
