@@ -122,7 +122,7 @@ class ClockSampler:
             self.proc.kill()
         self.tmp.flush()
         self.tmp.seek(0)
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in self.tmp.read().splitlines():
             f = [x.strip() for x in line.split(",")]
@@ -131,6 +131,7 @@ class ClockSampler:
             try:
                 sm.append(float(f[1]))
                 mx.append(float(f[2]))
+                pw.append(float(f[3]))
             except ValueError:
                 continue
             for name, val in zip(names, f[5:9]):
@@ -141,9 +142,14 @@ class ClockSampler:
         except OSError:
             pass
         if sm:
-            top = sorted(sm)[len(sm) // 2:]  # samples under load dominate the upper half
-            out["sm_mhz"] = float(np.median(top))
+            # samples under load = those drawing at least 60 % of the highest power seen (the sampler also catches the idle
+            # edges of the timed region; under the power cap the LOADED clock is the lower one)
+            top_pw = max(pw)
+            load = [c for c, w in zip(sm, pw) if w >= 0.6 * top_pw] or sm
+            out["sm_mhz"] = float(np.median(load))
             out["sm_max_mhz"] = float(max(mx))
+            out["power_w_max"] = top_pw
+            out["samples_under_load"] = len(load)
         out["reasons"] = sorted(reasons)
         out["samples"] = len(sm)
         return out
@@ -818,7 +824,7 @@ def main():
     if args.nq:
         wl["nq"] = args.nq
     if args.steps <= 0:  # long enough (>= ~0.2 s) for nvidia-smi to sample clocks inside the timed region
-        args.steps = {"cfg3": 20, "cfg2": 4000, "cfg4": 60, "cfg4b": 10, "cfg5": 3}[args.workload]
+        args.steps = {"cfg3": 60, "cfg2": 8000, "cfg4": 120, "cfg4b": 40, "cfg5": 3}[args.workload]
     if args.warmup <= 0:
         args.warmup = 3 if wl["mode"] == "tc" else 10
     args.warmup = max(args.warmup, 3)

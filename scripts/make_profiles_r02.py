@@ -31,7 +31,7 @@ def per_launch(path):
 # 1. launch list of one cfg3 search (serialised by ncu: compare shares, not absolutes)
 L = per_launch(os.path.join(G, "r02_launches_cfg3_raw.csv"))
 last = max(i for i, e in enumerate(L) if "tc_prep" in e["kernel"])
-search = L[last:last + 17]
+search = [e for e in L[last:last + 17] if not e["kernel"].startswith("at::")]
 with open(os.path.join(P, "r02_launches_cfg3.csv"), "w") as fh:
     fh.write("# one cfg3 search (10 M rows x 4096 queries, k=100), ncu --metrics gpu__time_duration.sum --clock-control none; kernels in launch order\n")
     fh.write("kernel,duration_us\n")
