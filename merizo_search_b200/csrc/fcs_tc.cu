@@ -56,11 +56,6 @@
 #include "fcs_internal.h"
 #include "fcs_tc.h"
 
-#ifndef FCS_TC_SLOWPATH
-#define FCS_TC_SLOWPATH 1  // 1: a hit's 8-column group is re-read from TMEM (default); 0: hits are taken from the registers of
-                           // the 32-column load -- measured 7-10 % SLOWER on every workload (profiles/r02_experiments.md): keeping
-                           // the 32 registers live past the threshold test keeps the next tcgen05.ld from being issued early
-#endif
 
 #ifndef FCS_TC_BPOLICY
 #define FCS_TC_BPOLICY 1  // L2 policy of the DB tile copies: 1 evict_normal (default: the CTAs that sweep the same tiles for other
@@ -290,7 +285,7 @@ __device__ __forceinline__ int64_t tile_of(const TcGemmParams& p, int64_t idx) {
 
 #ifdef FCS_TC_TRACE
 // debug build only: cycle stamps of CTA 0 (MMA thread: row 0/1; epilogue warp of tile 0, quadrant 2: rows 2..4)
-__device__ long long g_trace[5][256];
+__device__ long long g_trace[8][256];
 #define TRACE(row, idx, cond) do { if (p.trace_on && (cond) && (idx) < 256) g_trace[row][idx] = clock64(); } while (0)
 #else
 #define TRACE(row, idx, cond) do { } while (0)
@@ -385,6 +380,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_filter_kernel(const TcG
                     if (j + TC_PREFETCH < seg_len)
                         bulk_prefetch_l2(p.b_img + size_t(tile_of(p, ti + j + TC_PREFETCH)) * B_TILE_BYTES, B_TILE_BYTES);
                     mbar_wait(&empty_b[st], ph ^ 1u);
+                    TRACE(5, it, blockIdx.x == 0);
                     mbar_arrive_expect_tx(&full_b[st], B_TILE_BYTES);
                     bulk_g2s(sB + st * B_TILE_BYTES, p.b_img + size_t(tile_of(p, ti + j)) * B_TILE_BYTES, B_TILE_BYTES, &full_b[st], pol_stream);
                 }
@@ -410,6 +406,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_filter_kernel(const TcG
                     const uint32_t tph = it & 1u;
                     mbar_wait(&full_b[st], ph);
                     tc_fence_after();
+                    TRACE(6, it, blockIdx.x == 0 && t_first == 0);
 #pragma unroll
                     for (int tt = 0; tt < TC_QT / TC_MMA_WARPS; ++tt) {
                         const int t = t_first + tt;
@@ -485,94 +482,78 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_filter_kernel(const TcG
                 // rows of this tile that exist (the last tile of the shard is zero-padded)
                 const int64_t left = p.n_rows - row_base;
                 const int rows_here = left < TC_N ? int(left) : TC_N;
-                // Fast path: 32 scores per tcgen05.ld, reduced with 3-input max to one maximum per 8 columns, one compare
-                // against the threshold.  Slow path (some lane of the warp has a hit among these 32 columns): the scores
-                // are still in registers -- no second TMEM read; the 8-column maxima gate the column checks, so a hit costs
-                // ~50 issue slots of the warp.  That count is what matters: the 16 epilogue warps share the schedulers
-                // with the MMA issuers, and an epilogue that issues more than ~2 k instructions per tile step slows the
-                // GEMM itself (a version with 32 unconditional column checks per hit part ran the sweep 27 % slower).
-#if FCS_TC_SLOWPATH == 0
-#pragma unroll 1
+                // One accumulator buffer per tile: the tile's chain MMA -> epilogue -> next MMA sets the step period (pipeline
+                // trace in profiles/r02_experiments.md), so everything between "accumulator full" and "accumulator handed
+                // back" is on the critical path of the whole CTA.
+                //  * Fast pass: four 32-column tcgen05.ld, each reduced with 3-input max to one maximum per 8 columns; the
+                //    comparison results go into a 16-bit mask (bit 4*part + group) -- no warp vote inside the loop.  ONE warp
+                //    OR-reduction per tile then says whether any lane has a hit anywhere (rare once the threshold is warm).
+                //  * Slow path: the hit 8-column groups are re-read from TMEM (taking the values from the registers of the
+                //    32-column load instead was 7-10 % slower on every workload: the live registers delay the next load).
+                //  * Up to two hits per tile are parked in registers and appended AFTER the accumulator has been handed back:
+                //    the append's call, store and (every 16th time) L2 atomic are off the chain.  A third hit in one tile is
+                //    appended at once.  The append is not inlined: the loop has to stay instruction-cache resident.
+                int pend_n = 0;
+                uint32_t pend_v0 = 0, pend_v1 = 0;
+                int pend_c0 = 0, pend_c1 = 0;
+                unsigned gm = 0;
+#pragma unroll
                 for (int part = 0; part < TC_N / 32; ++part) {
                     uint32_t r[32];
                     tc_ld32(tmem_base + lane_base + uint32_t(t * TC_N + part * 32), r);
                     tc_wait_ld();
-                    const float* f = reinterpret_cast<const float*>(r);
-                    float m[4];
 #pragma unroll
-                    for (int g = 0; g < 4; ++g)
-                        m[g] = fmaxf(max3(f[g * 8], f[g * 8 + 1], f[g * 8 + 2]), max3(max3(f[g * 8 + 3], f[g * 8 + 4], f[g * 8 + 5]), f[g * 8 + 6], f[g * 8 + 7]));
-                    const float mx = fmaxf(max3(m[0], m[1], m[2]), m[3]);
-                    if (__any_sync(FULL, mx > thr)) {  // rare once the threshold is warm
-                        if (mx > thr) {
-#pragma unroll
-                            for (int g = 0; g < 4; ++g) {
-                                if (m[g] > thr) {
-#pragma unroll
-                                    for (int c = 0; c < 8; ++c) {
-                                        const int col = part * 32 + g * 8 + c;
-                                        if (f[g * 8 + c] > thr && col < rows_here)
-                                            res = tc_append(cnt_q, cand_q, res, p.res_block, r[g * 8 + c], uint32_t(row_base) + uint32_t(col), p.cap);
-                                    }
-                                }
-                            }
-                        }
-                        __syncwarp();
+                    for (int g = 0; g < 4; ++g) {
+                        const float* f = reinterpret_cast<const float*>(&r[g * 8]);
+                        const float mg = fmaxf(max3(f[0], f[1], f[2]), max3(max3(f[3], f[4], f[5]), f[6], f[7]));
+                        gm |= (mg > thr) ? (1u << (part * 4 + g)) : 0u;
                     }
                 }
-#else
-#pragma unroll 1
-                for (int part = 0; part < TC_N / 32; ++part) {
-                    const uint32_t taddr = tmem_base + lane_base + uint32_t(t * TC_N + part * 32);
-                    float m[4];
-                    {
-                        uint32_t r[32];
-                        tc_ld32(taddr, r);
-                        tc_wait_ld();
+                unsigned wgm = __reduce_or_sync(FULL, gm);
+                while (wgm) {  // slow path: re-read the hit 8-column groups from TMEM (warp-uniform loop)
+                    const int pg = __ffs(wgm) - 1;
+                    wgm &= wgm - 1;
+                    uint32_t v8[8];
+                    __syncwarp();  // lanes left the divergent loop below at different times
+                    tc_ld8(tmem_base + lane_base + uint32_t(t * TC_N + pg * 8), v8);
+                    tc_wait_ld();
+                    unsigned hits = 0;
 #pragma unroll
-                        for (int g = 0; g < 4; ++g) {
-                            const float* f = reinterpret_cast<const float*>(&r[g * 8]);
-                            m[g] = fmaxf(max3(f[0], f[1], f[2]), max3(max3(f[3], f[4], f[5]), f[6], f[7]));
-                        }
-                    }
-                    const float mx = fmaxf(max3(m[0], m[1], m[2]), m[3]);
-                    if (__any_sync(FULL, mx > thr)) {  // rare once the threshold is warm
-                        unsigned wgm = 0;  // groups in which some lane has a hit (warp-uniform)
+                    for (int c = 0; c < 8; ++c) hits |= (__uint_as_float(v8[c]) > thr) ? (1u << c) : 0u;
+                    while (hits) {
+                        const int c = __ffs(hits) - 1;
+                        hits &= hits - 1;
+                        uint32_t bits = v8[0];
 #pragma unroll
-                        for (int g = 0; g < 4; ++g) wgm |= __any_sync(FULL, m[g] > thr) ? (1u << g) : 0u;
-                        while (wgm) {
-                            const int g = __ffs(wgm) - 1;
-                            wgm &= wgm - 1;
-                            uint32_t v8[8];
-                            __syncwarp();  // lanes left the divergent append loop below at different times
-                            tc_ld8(taddr + uint32_t(g * 8), v8);
-                            tc_wait_ld();
-                            unsigned hits = 0;
-#pragma unroll
-                            for (int c = 0; c < 8; ++c) hits |= (__uint_as_float(v8[c]) > thr) ? (1u << c) : 0u;
-                            while (hits) {
-                                const int c = __ffs(hits) - 1;
-                                hits &= hits - 1;
-                                uint32_t bits = v8[0];
-#pragma unroll
-                                for (int cc = 1; cc < 8; ++cc) bits = (c == cc) ? v8[cc] : bits;
-                                const int col = part * 32 + g * 8 + c;
-                                if (col < rows_here) res = tc_append(cnt_q, cand_q, res, p.res_block, bits, uint32_t(row_base) + uint32_t(col), p.cap);
-                            }
+                        for (int cc = 1; cc < 8; ++cc) bits = (c == cc) ? v8[cc] : bits;
+                        const int col = pg * 8 + c;
+                        if (col >= rows_here) continue;  // zero padding rows of the shard's last tile
+                        if (pend_n == 0) {
+                            pend_v0 = bits;
+                            pend_c0 = col;
+                            pend_n = 1;
+                        } else if (pend_n == 1) {
+                            pend_v1 = bits;
+                            pend_c1 = col;
+                            pend_n = 2;
+                        } else {
+                            res = tc_append(cnt_q, cand_q, res, p.res_block, bits, uint32_t(row_base) + uint32_t(col), p.cap);
                         }
                     }
                 }
-#endif
                 TRACE(3, it, blockIdx.x == 0 && warp == 5 && lane == 0);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tmem_empty[t]);
+                if (pend_n > 0) res = tc_append(cnt_q, cand_q, res, p.res_block, pend_v0, uint32_t(row_base) + uint32_t(pend_c0), p.cap);
+                if (pend_n > 1) res = tc_append(cnt_q, cand_q, res, p.res_block, pend_v1, uint32_t(row_base) + uint32_t(pend_c1), p.cap);
                 TRACE(4, it, blockIdx.x == 0 && warp == 5 && lane == 0);
             }
             if (!p.first_round) tc_close_reservation(cand_q, res, p.res_block, p.cap);
             s += seg_len;
         }
     }
+
 
     tc_fence_before();
     __syncthreads();
@@ -1423,12 +1404,13 @@ int tc_search(TcState* s, const float* q_dev, int nq, int k, int kprime, int qno
 #ifdef FCS_TC_TRACE
     {
         TC_CUDA(cudaStreamSynchronize(stream));
-        static long long h[5][256];
+        static long long h[8][256];
         cudaMemcpyFromSymbol(h, g_trace, sizeof h);
-        fprintf(stderr, "[fcs_tc trace, CTA 0, cycles relative to first stamp]\n it  mma_ready mma_issued | epi_full epi_done epi_arrived\n");
-        for (int i = 100; i < 116; ++i)
-            fprintf(stderr, "%3d  %9lld %9lld | %9lld %9lld %9lld\n", i, h[0][i] - h[0][100], h[1][i] - h[0][100], h[2][i] - h[0][100],
-                    h[3][i] - h[0][100], h[4][i] - h[0][100]);
+        fprintf(stderr, "[fcs_tc trace, CTA 0, tile 0; cycles relative to iteration 100]\n"
+                        " it | producer: stage free | MMA: B tile landed, accumulator free, 8 MMAs issued | epilogue (warp 5): accumulator full, drained, after appends\n");
+        for (int i = 100; i < 124; ++i)
+            fprintf(stderr, "%3d | %8lld | %8lld %8lld %8lld | %8lld %8lld %8lld\n", i, h[5][i] - h[0][100], h[6][i] - h[0][100], h[0][i] - h[0][100],
+                    h[1][i] - h[0][100], h[2][i] - h[0][100], h[3][i] - h[0][100], h[4][i] - h[0][100]);
     }
 #endif
     return FCS_OK;
