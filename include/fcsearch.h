@@ -126,7 +126,8 @@ int fcs_search_device(fcs_db* db, const float* q_dev, int nq, const int32_t* qle
 /* Synchronises `stream` (NULL = the handle's own) and, if the last fcs_search_device queued more
  * than FCS_ASYNC_FALLBACK_QUERIES queries for the exact scan, scans the rest into the same output
  * buffers (which must still be valid) and waits.  *out_queued (optional) = length of that queue.
- * Cheap when there is nothing to do; fcs_search does this itself. */
+ * `stream` must be the stream the search was enqueued on.  Cheap when there is nothing to do; fcs_search
+ * does this itself. */
 int fcs_search_finish(fcs_db* db, void* stream, int* out_queued);
 /* Enqueues on `stream` a copy of the last fcs_search_device's fallback-queue length (uint32) into DEVICE memory at
  * dst_dev_u32, so that a multi-rank host can ship it with the key lists (one collective) and learn after its one

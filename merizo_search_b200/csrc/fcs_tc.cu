@@ -32,7 +32,7 @@
 //   each followed by tc_select_kernel (one block per query, radix select on the order-preserving score word), and each
 //   GEMM round after the first launched programmatically behind its selection kernel (setup and operand prefetch overlap
 //   the selection's tail).  Every tile is multiplied exactly once.  cfg3 (10 M rows x 4096 queries) runs 5 GEMM launches:
-//   16 / 92 / 617 / 4158 tiles of samples (0.9 ms, 6 % of the rows) and a 73 k-tile sweep (7.3 ms) -- where round 1's
+//   16 / 92 / 617 / 4158 tiles of samples (0.8 ms, 6 % of the rows) and a 73 k-tile sweep (6.8 ms) -- where round 1's
 //   geometric rounds (x3 rows per round at 2k' hits each) needed 9 launches and 2.8 ms for the first 2.2 M rows.
 //
 //   K4  tc_rescore_kernel -- one block (4 warps) per query.  Phase A: the k' best approximate candidates are gathered

@@ -35,3 +35,43 @@ def test_reference_arm_embed_line():
     d = _run("--workload", "embed", "--nq", "4")
     assert d["impl"] == "reference" and d["unit"] == "structures/s" and d["value"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_both_arms_print_the_same_config_keys():
+    """The driver compares the `config` of the two arms: the reference line must carry the keys of the GPU line."""
+    sys.path.insert(0, ROOT)
+    import bench
+
+    wl = dict(bench.WORKLOADS["cfg3"])
+    qg, shards = bench.layout(wl, wl["rows"], 8, 0)
+    assert (qg, shards) == (8, 1)                                   # a 7.7 GB database is replicated, the batch split
+    assert bench.layout(wl, wl["rows"], 8, 1) == (1, 8)             # --query-groups 1: pure row sharding
+    assert bench.layout(bench.WORKLOADS["cfg4"], 365_000_000, 8, 0) == (1, 8)  # TED-scale slices are never replicated
+    gpu_cfg = bench.make_config(wl, "cfg3", wl["rows"], wl["rows"], 8, shards, qg, 512,
+                                {"db_load_s": 1.0, "tc_fallback_queries": 0, "tc_rounds": 5})
+    d = _run("--workload", "cfg3", "--rows", "300000", "--steps", "1", "--warmup", "3")
+    assert set(d["config"]) == set(gpu_cfg)
+    assert d["config"]["workload"] == "cfg3" and d["config"]["rows_total"] == 300000 and d["config"]["k"] == 100
+
+
+def test_synthetic_database_is_one_global_block_matrix():
+    """Shards take slices of GLOBAL 2^20-row blocks (block seed = base + block id), so a row's content does not depend on
+    how many ranks there are -- the planted-row parity check and the brute force rely on it."""
+    sys.path.insert(0, ROOT)
+    import bench
+
+    blk = 1 << 20
+    rows_total = 10_000_000
+    for world in (1, 2, 8):
+        per = -(-rows_total // world)
+        seen = []
+        for r in range(world):
+            r0, r1 = min(rows_total, r * per), min(rows_total, (r + 1) * per)
+            for gb, nrows_b, lo, hi in bench.shard_blocks(r0, r1, rows_total, blk):
+                assert 0 <= lo < hi <= nrows_b <= blk
+                seen.append((gb * blk + lo, gb * blk + hi))
+        seen.sort()
+        assert seen[0][0] == 0 and seen[-1][1] == rows_total
+        assert all(a[1] == b[0] for a, b in zip(seen, seen[1:]))
+    ids = bench.planted_ids(rows_total)
+    assert len(ids) == bench.PLANTED and len({i * 8 // rows_total for i in ids}) == 8  # one planted row in every eighth
