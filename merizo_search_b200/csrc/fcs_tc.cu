@@ -451,10 +451,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_filter_kernel(const TcG
             uint2 res = make_uint2(0u, ~0u);
             for (int64_t j = 0; j < seg_len; ++j, ++it) {
                 const uint32_t tph = it & 1u;
+                // the tile's first row does not depend on the accumulator: computed BEFORE the wait (the complement
+                // mapping of the sweep has a 64-bit division; after the wait it sat on the tile's critical chain)
+                int64_t row_base = tile_of(p, ti + j) * TC_N;
+                asm volatile("" : "+l"(row_base));
+                const int64_t left = p.n_rows - row_base;
+                int rows_here = left < TC_N ? int(left) : TC_N;  // the last tile of the shard is zero-padded
+                asm volatile("" : "+r"(rows_here));  // materialise it here: volatile statements keep their order
                 mbar_wait(&tmem_full[t], tph);
                 tc_fence_after();
                 TRACE(2, it, blockIdx.x == 0 && warp == 5 && lane == 0);
-                const int64_t row_base = tile_of(p, ti + j) * TC_N;
                 if (p.first_round) {
                     // round 0: every score is recorded, slot = row of the sample (no threshold, no atomics)
                     uint64_t* dst = cand_q + (ti + j) * TC_N;
@@ -479,9 +485,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_filter_kernel(const TcG
                     if (lane == 0) mbar_arrive(&tmem_empty[t]);
                     continue;
                 }
-                // rows of this tile that exist (the last tile of the shard is zero-padded)
-                const int64_t left = p.n_rows - row_base;
-                const int rows_here = left < TC_N ? int(left) : TC_N;
                 // One accumulator buffer per tile: the tile's chain MMA -> epilogue -> next MMA sets the step period (pipeline
                 // trace in profiles/r02_experiments.md), so everything between "accumulator full" and "accumulator handed
                 // back" is on the critical path of the whole CTA.
