@@ -29,7 +29,7 @@ NVCC_FLAGS = [
     "-cudart", "static",
 ] + (["-DFCS_TC_TRACE"] if os.environ.get("FCS_TC_TRACE") else []) + \
     ([f"-DFCS_TC_SLOWPATH={int(os.environ['FCS_TC_SLOWPATH'])}"] if os.environ.get("FCS_TC_SLOWPATH") else []) + \
-    [f"-D{k}={int(v)}" for k, v in sorted(os.environ.items()) if k.startswith("FCS_TC_") and k in ("FCS_TC_BPOLICY", "FCS_TC_EPI", "FCS_TC_PARK", "FCS_TC_VOTE")]
+    [f"-D{k}={int(v)}" for k, v in sorted(os.environ.items()) if k.startswith("FCS_TC_") and k in ("FCS_TC_BPOLICY",)]
 # experiments: FCS_LIB_VARIANT=name builds/loads libfcsearch_<name>.so next to the default library
 _VARIANT = os.environ.get("FCS_LIB_VARIANT", "")
 if _VARIANT:
