@@ -141,8 +141,19 @@ def device_count() -> int:
     return n.value
 
 
+_addressof, _char_from_buffer = C.addressof, C.c_char.from_buffer
+
+
 def _np_ptr(a: Optional[np.ndarray]):
-    return None if a is None else a.ctypes.data_as(C.c_void_p)
+    """Address of an array's first byte, for a c_void_p parameter.  `ndarray.ctypes` costs 4 us per use (20 us per search
+    call, a quarter of a single-query search); the buffer protocol gives the address in 0.8 us.  Read-only or empty arrays
+    (np.memmap opened 'r', zero rows) take the slow way."""
+    if a is None:
+        return None
+    try:
+        return _addressof(_char_from_buffer(a))
+    except (TypeError, ValueError, BufferError):
+        return a.ctypes.data
 
 
 def _out_arrays(out, nq: int, k: int):
