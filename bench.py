@@ -763,9 +763,10 @@ def run_gpu(args, wl, wl_name, steps=None, warmup=None):
             "scaling": wl["scaling"], "vs_baseline": None,
             "dtype": "bf16 tensor-core contraction + fp32 exact rescore" if wl["mode"] == "tc" else "f32",
             "data": "synthetic (i.i.d. N(0,1) rows, L2-normalised, generated on device per 2^20-row block; random unit queries)",
-            "config": make_config(wl, wl_name, rows_total, n_local, world, n_shards, qg, nq_local,
-                                  {"db_load_s": round(t_load, 2), "tc_fallback_queries": int(timing.last_tc_fallbacks),
-                                   "tc_rounds": int(timing.last_rounds)}),
+            # `config` describes the workload only and is identical, key for key and value for value, on the reference arm;
+            # what this run measured about itself goes into `run`
+            "config": make_config(wl, wl_name, rows_total, n_local, world, n_shards, qg, nq_local),
+            "run": {"db_load_s": round(t_load, 2), "tc_fallback_queries": int(timing.last_tc_fallbacks), "tc_rounds": int(timing.last_rounds)},
             "parity_checked": bool(parity["ok"]), "parity": parity,
             "e2e": {"value": nq / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": int(nq * 512),
                     "d2h_bytes_per_step": int(nq * k * 12), "ms_per_step": e2e_s * 1e3,
@@ -848,7 +849,7 @@ def main():
             "higher_is_better": True, "scaling": wl["scaling"], "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             # same keys and values as the GPU arm's config (the layout fields describe the GPU arm this line is compared with)
             "config": make_config(wl, args.workload, rows_total, -(-rows_total // ref_shards), world, ref_shards, ref_qg,
-                                  -(-wl["nq"] // ref_qg), {"db_load_s": None, "tc_fallback_queries": 0, "tc_rounds": 0}),
+                                  -(-wl["nq"] // ref_qg)),
             "cpu_baseline": {"value": v, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }))
@@ -869,7 +870,7 @@ def main():
                 o, _ = run_gpu(args, WORKLOADS[w], w, steps={"cfg4": 40, "cfg4b": 8, "cfg2": 2000, "cfg3": 10, "cfg5": 3}[w],
                                warmup=3 if w == "cfg5" else 5)
                 if rank == 0:
-                    extra[w] = {key: o[key] for key in ("value", "unit", "ms_per_step", "scaling", "e2e", "roofline", "config", "gpu_launches",
+                    extra[w] = {key: o[key] for key in ("value", "unit", "ms_per_step", "scaling", "e2e", "roofline", "config", "run", "gpu_launches",
                                                         "parity_checked", "parity")}
             except Exception as exc:  # an extra must never take the primary line down
                 if rank == 0:

@@ -7,7 +7,7 @@ run() {
 import json,sys
 try:
     d=json.loads(sys.stdin.read().strip().splitlines()[-1])
-    print('$label: %.3f ms/step  %.0f q/s  e2e %.0f K3 frac %.3f fallbacks %d parity %s' % (d['ms_per_step'], d['value'], d['e2e']['value'], d['roofline']['frac'], d['config']['tc_fallback_queries'], d['parity_checked']))
+    print('$label: %.3f ms/step  %.0f q/s  e2e %.0f K3 frac %.3f fallbacks %d parity %s' % (d['ms_per_step'], d['value'], d['e2e']['value'], d['roofline']['frac'], d['run']['tc_fallback_queries'], d['parity_checked']))
 except Exception as e:
     print('$label: FAILED', e)"
 }

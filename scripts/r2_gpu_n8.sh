@@ -8,7 +8,7 @@ show() { python -c "
 import json,sys
 try:
     d=json.loads(open('$1').read().strip().splitlines()[-1])
-    print('$1: n=%d %.3f ms/step %.0f q/s e2e %.0f frac %.3f parity %s fb %s | %s' % (d['n_gpus'], d['ms_per_step'], d['value'], d['e2e']['value'], d['roofline']['frac'], d['parity_checked'], d['config']['tc_fallback_queries'], d['config']['parallelism']))
+    print('$1: n=%d %.3f ms/step %.0f q/s e2e %.0f frac %.3f parity %s fb %s | %s' % (d['n_gpus'], d['ms_per_step'], d['value'], d['e2e']['value'], d['roofline']['frac'], d['parity_checked'], d['run']['tc_fallback_queries'], d['config']['parallelism']))
     for k,v in d.get('extra',{}).items(): print('   ', k, v.get('value'), v.get('ms_per_step'), (v.get('e2e') or {}).get('value'), v.get('parity_checked'), (v.get('roofline') or {}).get('frac'), v.get('error'))
 except Exception as e:
     print('$1 FAILED', e)

@@ -47,10 +47,10 @@ def test_both_arms_print_the_same_config_keys():
     assert (qg, shards) == (8, 1)                                   # a 7.7 GB database is replicated, the batch split
     assert bench.layout(wl, wl["rows"], 8, 1) == (1, 8)             # --query-groups 1: pure row sharding
     assert bench.layout(bench.WORKLOADS["cfg4"], 365_000_000, 8, 0) == (1, 8)  # TED-scale slices are never replicated
-    gpu_cfg = bench.make_config(wl, "cfg3", wl["rows"], wl["rows"], 8, shards, qg, 512,
-                                {"db_load_s": 1.0, "tc_fallback_queries": 0, "tc_rounds": 5})
     d = _run("--workload", "cfg3", "--rows", "300000", "--steps", "1", "--warmup", "3")
-    assert set(d["config"]) == set(gpu_cfg)
+    wl["rows"] = 300000
+    gpu_cfg = bench.make_config(wl, "cfg3", 300000, 300000, 1, 1, 1, wl["nq"])  # what run_gpu() puts into its line at N=1
+    assert d["config"] == gpu_cfg                                   # identical, key for key and value for value
     assert d["config"]["workload"] == "cfg3" and d["config"]["rows_total"] == 300000 and d["config"]["k"] == 100
 
 
