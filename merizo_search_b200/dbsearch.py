@@ -193,6 +193,9 @@ def load_resident_file(path: str, n_rows: int, device=None) -> ResidentDatabase:
         return resident
     if os.path.getsize(path) < n_rows * DIM * 4:
         raise native.FcsError(native.ERR_INVALID, f"{path}: {os.path.getsize(path)} bytes cannot hold {n_rows} x {DIM} fp32 rows")
+    if device is not None and not _is_cuda(device):
+        raise native.FcsError(native.ERR_UNSUPPORTED, f"merizo_search_b200: device {device!r} is not a CUDA device and this path has no "
+                                                      "CPU implementation (use the reference's own dbsearch_faiss)")
     remote = serve.connect(path, "faiss")  # FCS_SERVER: a resident copy in another process (serve.py)
     if remote is not None:
         resident = ResidentDatabase(remote, "faiss")

@@ -89,3 +89,13 @@ def test_dbsearch_faiss_driver_logic_with_oracle_engine(tiny_faiss_db, tmp_path,
                                          network, topk=3, mincov=0.7, mincos=1.5, mintm=0.5, fastmode=True,
                                          device=torch.device("cpu"), inputs_are_ca=True, skip_tmalign=True)
     assert r2 == [] and a2 == []
+
+
+def test_faiss_flavour_refuses_a_non_cuda_device(tiny_faiss_db):
+    """-d cpu must not silently put the database on the GPUs (nor fall back to a CPU path that does not exist)."""
+    d, emb, *_ = tiny_faiss_db
+    b200._RESIDENT.clear()
+    with pytest.raises(native.FcsError):
+        b200.load_resident_file(str(d / "t_raw_128d_norm.db"), emb.shape[0], torch.device("cpu"))
+    with pytest.raises(native.FcsError):  # a file too short for the advertised row count
+        b200.load_resident_file(str(d / "t_raw_128d_norm.db"), emb.shape[0] + 1, "cuda")
