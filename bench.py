@@ -265,8 +265,9 @@ def run_embed(args, steps=3, warmup=3, cpu_baseline=True):
     structures = synth.synthetic_chains(lens, seed=wl["chain_seed"])
     sd = synth.synthetic_state_dict(wl["weight_seed"])
     emb = b200_embed.FoldClassEmbedder(sd, device=local_rank)
-    tc_mode = os.environ.get("FCS_EMBED_MODE", "1") != "0"  # the library's default: tcgen05 (bf16 hi/lo split); 0 = fp32 FMA pipe
-    emb._emb.set_mode(native.EMBED_MODE_TC if tc_mode else native.EMBED_MODE_FP32)
+    mode = int(os.environ.get("FCS_EMBED_MODE", str(native.EMBED_MODE_TC3)))  # the library's default: tcgen05 (bf16 hi/lo split), 16 generator warps
+    tc_mode = mode != native.EMBED_MODE_FP32                                   # 0 = fp32 FMA pipe
+    emb._emb.set_mode(mode)
     coords, offsets = native.Embedder._pack(structures)
     out_dev = torch.empty((n, 128), dtype=torch.float32, device=torch.device("cuda", local_rank))
     torch.cuda.synchronize()
@@ -297,7 +298,7 @@ def run_embed(args, steps=3, warmup=3, cpu_baseline=True):
         # reported beside it
         peaks = load_peaks()
         roof = {"bound": "tensor", "achieved": fp32_equiv, "peak": peaks["tensor"], "unit": "TFLOP/s", "frac": fp32_equiv / peaks["tensor"],
-                "traffic": None, "kernel": "embed_edge_tc_kernel (both layers of one batch)",
+                "traffic": None, "kernel": ("embed_edge_tc_kernel" if mode == native.EMBED_MODE_TC else "embed_edge_tc2_kernel") + " (both layers of one batch)",
                 "algorithmic": "2*514*256 flop per (i,j) pair per layer (fp32-grade result)",
                 "issued_mma_tflops": 3.0 * fp32_equiv, "issued_mma_frac": 3.0 * fp32_equiv / peaks["tensor"],
                 "peak_burst": peaks["tensor_burst"], "frac_burst": fp32_equiv / peaks["tensor_burst"],

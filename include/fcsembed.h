@@ -69,11 +69,17 @@ int fcs_embed(fcs_embedder* e, const float* coords, const int64_t* offsets, int 
 int fcs_embed_to_device(fcs_embedder* e, const float* coords, const int64_t* offsets, int n_structures, float* out_dev);
 
 /* Which kernel evaluates the O(L^2) edge MLP:
- *   FCS_EMBED_MODE_TC    tcgen05 tensor cores, bf16 hi/lo split operands, three products, fp32 accumulation in TMEM
- *                        (fp32-grade accuracy: the same parity tolerance applies); the default
+ *   FCS_EMBED_MODE_TC3   tcgen05 tensor cores, bf16 hi/lo split operands, three products, fp32 accumulation in TMEM
+ *                        (fp32-grade accuracy: the same parity tolerance applies); 16 operand-generator warps, dedicated
+ *                        epilogue warps, two accumulator buffers (a tile's MMAs run under the previous tile's epilogue);
+ *                        the default
+ *   FCS_EMBED_MODE_TC2   same structure with 8 generator warps
+ *   FCS_EMBED_MODE_TC    the round-1 tensor-core kernel (generators also run the epilogue, one accumulator buffer)
  *   FCS_EMBED_MODE_FP32  fp32 FMA pipe (packed FFMA2) */
 #define FCS_EMBED_MODE_FP32 0
 #define FCS_EMBED_MODE_TC 1
+#define FCS_EMBED_MODE_TC2 2
+#define FCS_EMBED_MODE_TC3 3
 int fcs_embed_set_mode(fcs_embedder* e, int mode);
 
 int fcs_embed_get_timing(const fcs_embedder* e, fcs_embed_timing* out);

@@ -19,7 +19,10 @@
 //
 //   K_e0 embed_init_feats_kernel   f = pe[:L]                          (PositionalEncoder.forward)
 //   K_e1 embed_node_proj_kernel    P, Q  [R, 528] (514 padded to 33 x 16)
-//   K_e2 embed_edge_tc_kernel      m_i   [R, 256]   <- dominant; tcgen05 (default): 3 x 2*514*256 bf16 flop per (i,j) pair
+//   K_e2 embed_edge_tc2_kernel<16> m_i   [R, 256]   <- dominant; tcgen05 (default, FCS_EMBED_MODE_TC3): 3 x 2*514*256 bf16
+//                                                     flop per (i,j) pair; generators / MMA issuer / epilogue in separate
+//                                                     warps, two TMEM accumulator buffers
+//        embed_edge_tc_kernel                          round-1 tcgen05 kernel (FCS_EMBED_MODE_TC)
 //        embed_edge_kernel                             fp32 FMA-pipe variant (FCS_EMBED_MODE_FP32): 2*514*256 flop per pair
 //   K_e3 embed_node_mlp_kernel     f'    [R, 128]
 //   K_e4 embed_mean_kernel         mean over residues -> [n, 128]
@@ -103,14 +106,16 @@ __global__ void __launch_bounds__(256) embed_init_feats_kernel(const float* __re
 // out[r][c] = bias[c] + sum_k f[r][k] * wt[k][c]   for 16 residues per CTA; c < ncols (thread per column).
 // Used for P|Q (wt = [128][1056]: W1a^T | W1b^T, split into two [R][528] outputs) -- FLOPs are ~0.1 % of K_e2.
 constexpr int NP_ROWS = 16;
+// The feature tile is stored TRANSPOSED, [k][16 residues], so the 16 operands of a k-step are 4 broadcast LDS.128 instead of
+// 16 LDS.32 (the round-1 kernel was bound by those loads).
 __global__ void __launch_bounds__(256) embed_node_proj_kernel(const float* __restrict__ feats, int n_res,
                                                               const float* __restrict__ wt, const float* __restrict__ bias,
                                                               float* __restrict__ outP, float* __restrict__ outQ) {
-    __shared__ float sF[NP_ROWS][EW];
+    __shared__ __align__(16) float sFt[EW][NP_ROWS];
     const int r0 = blockIdx.x * NP_ROWS;
     for (int e = threadIdx.x; e < NP_ROWS * EW; e += blockDim.x) {
-        const int r = e / EW, k = e % EW;
-        sF[r][k] = (r0 + r < n_res) ? feats[size_t(r0 + r) * EW + k] : 0.f;
+        const int r = e / EW, k = e % EW;  // coalesced global read, transposed shared write
+        sFt[k][r] = (r0 + r < n_res) ? feats[size_t(r0 + r) * EW + k] : 0.f;
     }
     __syncthreads();
     for (int c = threadIdx.x; c < 2 * EHP; c += blockDim.x) {
@@ -121,8 +126,15 @@ __global__ void __launch_bounds__(256) embed_node_proj_kernel(const float* __res
 #pragma unroll 4
         for (int k = 0; k < EW; ++k) {
             const float w = wt[size_t(k) * (2 * EHP) + c];
+            const float4* f4 = reinterpret_cast<const float4*>(&sFt[k][0]);
 #pragma unroll
-            for (int r = 0; r < NP_ROWS; ++r) acc[r] = fmaf(sF[r][k], w, acc[r]);
+            for (int r4 = 0; r4 < NP_ROWS / 4; ++r4) {
+                const float4 f = f4[r4];
+                acc[4 * r4 + 0] = fmaf(f.x, w, acc[4 * r4 + 0]);
+                acc[4 * r4 + 1] = fmaf(f.y, w, acc[4 * r4 + 1]);
+                acc[4 * r4 + 2] = fmaf(f.z, w, acc[4 * r4 + 2]);
+                acc[4 * r4 + 3] = fmaf(f.w, w, acc[4 * r4 + 3]);
+            }
         }
         float* out = (c < EHP) ? outP : outQ;
         const int cc = (c < EHP) ? c : c - EHP;
@@ -654,21 +666,295 @@ __global__ void __launch_bounds__(TC_THREADS_ALL, 1) embed_edge_tc_kernel(const 
     }
 }
 
+// ------------------------------------------------------------------------------------------------ K_e2 (tensor cores, v2)
+// FCS_EMBED_MODE_TC2 (8 generator warps) and FCS_EMBED_MODE_TC3 (16 generator warps; the default since round 2: 24.0 k
+// structures/s vs 23.4 k for TC2 and 21.2 k for embed_edge_tc_kernel, parity identical -- scripts/embed_candidates.py).
+// Same math and operand pipeline as embed_edge_tc_kernel; what changes is who does the epilogue and when:
+//   warps 0..7   generators only (they never touch TMEM): after a tile's 17 chunks they go straight to the next tile
+//   warp  8      W2 image stream + MMA issue; two 256-column accumulators (all 512 TMEM columns): tile t accumulates into
+//                buffer t & 1, so the MMAs of tile t+1 run while tile t is being drained
+//   warps 9..16  epilogue (warp = TMEM lane quadrant x channel half).  120 registers per thread at 544 threads do not hold
+//                128 activations, so the tile is drained in two passes of tcgen05.ld: pass A accumulates the gate dot
+//                product (SiLU values are dropped), pass B recomputes SiLU, applies the gate and transpose-reduces 32
+//                channels at a time over the 16 lanes that hold the tile's 16 residues j.
+// Per-tile shared state read by the epilogue (validity mask) is double-buffered by tile parity; the generators wait for
+// the epilogue of tile t before they overwrite the mask of tile t+2.
+constexpr int TC2_EPI_WARPS = 8;
+__host__ __device__ constexpr int tc2_threads(int gen_warps) { return (gen_warps + 1 + TC2_EPI_WARPS) * 32; }  // 544 (8 generator warps) / 800 (16)
+constexpr int TC2F_VALID2 = TCF_FLOATS;                 // second validity buffer (tile parity 1) behind the v1 float region
+constexpr int TC2F_FLOATS = TC2F_VALID2 + TP;
+constexpr int EDGE_TC2_SMEM = TC_OPERAND_BYTES + TC2F_FLOATS * 4 + 16 * 8;
+static_assert(EDGE_TC2_SMEM <= 232448 && (TC2F_FLOATS * 4) % 8 == 0, "shared memory budget / barrier alignment");
+
+// GW = generator warps: 8 (thread = pair row x 16 hidden units per chunk) or 16 (x 8 hidden units: twice the warps to hide
+// the activation chain's latency; 80 registers per thread at 800 threads)
+template <int GW>
+__global__ void __launch_bounds__(tc2_threads(GW), 1) embed_edge_tc2_kernel(const EdgeParams p) {
+    constexpr int TC2_GEN_WARPS = GW;
+    constexpr int TC2_THREADS = tc2_threads(GW);
+    constexpr int GEN_THREADS = GW * 32;
+    constexpr int K8_PER_THREAD = 4 / (GW / 4);  // core-matrix columns (8 hidden units) per thread and chunk
+    extern __shared__ __align__(1024) uint8_t smraw[];
+    uint8_t* sB = smraw;
+    uint8_t* sA = smraw + B_STAGES * B_STAGE;
+    float* fl = reinterpret_cast<float*>(smraw + TC_OPERAND_BYTES);
+    float* sP = fl + TCF_P;
+    float* sQ = fl + TCF_Q;
+    float* sWd = fl + TCF_WD;
+    float* sMsum = fl + TCF_MSUM;
+    float* sGp = fl + TCF_GP;
+    float* sD2 = fl + TCF_D2;
+    float* sB2 = fl + TCF_B2;
+    float* sWg = fl + TCF_WG;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(fl + TC2F_FLOATS);
+    uint64_t* b_full = bars;          // [3]
+    uint64_t* mma_done = bars + 3;    // [3]
+    uint64_t* a_full = bars + 6;      // [3]
+    uint64_t* tmem_full = bars + 9;   // [2] all MMAs of the tile in accumulator buffer b have completed
+    uint64_t* tmem_empty = bars + 11; // [2] the 8 epilogue warps have drained buffer b (and are done with its validity mask)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int2 item = p.items[blockIdx.x];
+    const int start = p.s_start[item.x], L = p.s_len[item.x], i0 = item.y;
+    const int n_tiles = (L + TJ - 1) / TJ;
+    const uint32_t total_chunks = uint32_t(n_tiles) * NCH_T;
+
+    if (tid == 0) {
+        for (int i = 0; i < TC_STAGES; ++i) {
+            mbar_init(&b_full[i], 1);
+            mbar_init(&mma_done[i], 1);
+            mbar_init(&a_full[i], TC2_GEN_WARPS);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tmem_full[i], 1);
+            mbar_init(&tmem_empty[i], TC2_EPI_WARPS);
+        }
+        mbar_fence_init();
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (int e = tid; e < TI * (EHT / 4); e += TC2_THREADS) {
+        const int r = e / (EHT / 4), c4 = e % (EHT / 4);
+        const int row = start + min(i0 + r, L - 1);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c4 < EHP / 4) v = reinterpret_cast<const float4*>(p.P + size_t(row) * EHP)[c4];
+        reinterpret_cast<float4*>(sP)[r * (EHT / 4) + c4] = v;
+    }
+    for (int e = tid; e < EHT; e += TC2_THREADS) sWd[e] = (e < EHP) ? p.wd[e] : 0.f;
+    for (int e = tid; e < EM; e += TC2_THREADS) {
+        sB2[e] = p.b2[e];
+        sWg[e] = p.wg[e];
+    }
+    for (int e = tid; e < TI * EM; e += TC2_THREADS) sMsum[e] = 0.f;
+    tcg_fence_before();
+    __syncthreads();
+    tcg_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == TC2_GEN_WARPS) {
+        // ---------------------------------------------------------------- W2 image stream + MMA issue (one thread)
+        if (lane == 0) {
+            const uint64_t pol_keep = policy_evict_normal();
+            mbar_arrive_expect_tx(&b_full[0], B_STAGE);
+            bulk_g2s(sB, p.w2img, B_STAGE, &b_full[0], pol_keep);
+            uint32_t g = 0;
+            for (int t = 0; t < n_tiles; ++t) {
+                const uint32_t buf = uint32_t(t) & 1u;
+                const uint32_t d_tmem = tmem_base + buf * uint32_t(EM);
+                // the epilogue of tile t-2 has drained this accumulator buffer
+                mbar_wait(&tmem_empty[buf], ((uint32_t(t) >> 1) & 1u) ^ 1u);
+                tcg_fence_after();
+                for (int c = 0; c < NCH_T; ++c, ++g) {
+                    const uint32_t st = g % TC_STAGES, use = g / TC_STAGES;
+                    if (g + 1 < total_chunks) {
+                        const uint32_t st1 = (g + 1) % TC_STAGES, use1 = (g + 1) / TC_STAGES;
+                        const int c1 = (c + 1 == NCH_T) ? 0 : c + 1;
+                        mbar_wait(&mma_done[st1], (use1 & 1u) ^ 1u);
+                        mbar_arrive_expect_tx(&b_full[st1], B_STAGE);
+                        bulk_g2s(sB + st1 * B_STAGE, p.w2img + size_t(c1) * B_STAGE, B_STAGE, &b_full[st1], pol_keep);
+                    }
+                    mbar_wait(&a_full[st], use & 1u);
+                    mbar_wait(&b_full[st], use & 1u);
+                    tcg_fence_after();
+                    const uint32_t a_addr = smem_u32(sA + st * A_STAGE), b_addr = smem_u32(sB + st * B_STAGE);
+#pragma unroll
+                    for (int ks = 0; ks < KT / 16; ++ks) {
+                        const uint64_t ah = tc_desc(a_addr + ks * 256), al = tc_desc(a_addr + A_PART + ks * 256);
+                        const uint64_t bh = tc_desc(b_addr + ks * 256), bl = tc_desc(b_addr + B_PART + ks * 256);
+                        tcg_mma(d_tmem, ah, bh, (c > 0 || ks > 0) ? 1u : 0u);
+                        tcg_mma(d_tmem, al, bh, 1u);
+                        tcg_mma(d_tmem, ah, bl, 1u);
+                    }
+                    tcg_commit(&mma_done[st]);
+                }
+                tcg_commit(&tmem_full[buf]);  // arrives when every MMA issued so far (the whole tile) has completed
+            }
+        }
+        __syncwarp();
+    } else if (warp < TC2_GEN_WARPS) {
+        // ---------------------------------------------------------------- generators (thread = pair row x 16 hidden units)
+        const int g_row = tid & (TP - 1), g_kq = tid >> 7;  // g_kq: 0..GW/4-1
+        const int g_il = g_row >> 4, g_jl = g_row & (TJ - 1);
+        const uint32_t a_row_off = uint32_t(g_row >> 3) * 512u + uint32_t(g_row & 7) * 16u;
+        uint32_t g = 0;
+        for (int t = 0; t < n_tiles; ++t) {
+            const int j0 = t * TJ;
+            float* sValidT = (t & 1) ? (fl + TC2F_VALID2) : (fl + TCF_VALID);
+            // the epilogue of tile t-2 is done with this parity's validity mask (same event that frees its accumulator)
+            mbar_wait(&tmem_empty[t & 1], ((uint32_t(t) >> 1) & 1u) ^ 1u);
+            for (int e = tid; e < TJ * (EHT / 4); e += GEN_THREADS) {
+                const int r = e / (EHT / 4), c4 = e % (EHT / 4);
+                const int row = start + min(j0 + r, L - 1);
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (c4 < EHP / 4) v = reinterpret_cast<const float4*>(p.Q + size_t(row) * EHP)[c4];
+                *reinterpret_cast<float4*>(sQ + r * QST + c4 * 4) = v;
+            }
+            if (tid < TP) {
+                const int il = tid >> 4, jl = tid & (TJ - 1);
+                const int ri = start + min(i0 + il, L - 1), rj = start + min(j0 + jl, L - 1);
+                const float dx = p.coords[size_t(ri) * 3 + 0] - p.coords[size_t(rj) * 3 + 0];
+                const float dy = p.coords[size_t(ri) * 3 + 1] - p.coords[size_t(rj) * 3 + 1];
+                const float dz = p.coords[size_t(ri) * 3 + 2] - p.coords[size_t(rj) * 3 + 2];
+                const float dist = sqrtf(dx * dx + dy * dy + dz * dz);
+                sD2[tid] = dist * dist;
+                sValidT[tid] = (i0 + il < L && j0 + jl < L) ? 1.f : 0.f;
+            }
+            named_bar_sync(1, GEN_THREADS);
+            const float g_d2 = sD2[g_row];
+#pragma unroll 1
+            for (int c = 0; c < NCH_T; ++c, ++g) {
+                const uint32_t st = g % TC_STAGES;
+                mbar_wait(&mma_done[st], ((g / TC_STAGES) & 1u) ^ 1u);
+                uint8_t* a_hi = sA + st * A_STAGE;
+#pragma unroll
+                for (int u = 0; u < K8_PER_THREAD; ++u) {
+                    const int k8 = g_kq * K8_PER_THREAD + u;
+                    const int kg = c * KT + k8 * 8;
+                    const float4 pa = *reinterpret_cast<const float4*>(sP + g_il * EHT + kg);
+                    const float4 pb = *reinterpret_cast<const float4*>(sP + g_il * EHT + kg + 4);
+                    const float4 qa = *reinterpret_cast<const float4*>(sQ + g_jl * QST + kg);
+                    const float4 qb = *reinterpret_cast<const float4*>(sQ + g_jl * QST + kg + 4);
+                    const float4 wa = *reinterpret_cast<const float4*>(sWd + kg);
+                    const float4 wb = *reinterpret_cast<const float4*>(sWd + kg + 4);
+                    const float x[8] = {fmaf(g_d2, wa.x, pa.x + qa.x), fmaf(g_d2, wa.y, pa.y + qa.y), fmaf(g_d2, wa.z, pa.z + qa.z),
+                                        fmaf(g_d2, wa.w, pa.w + qa.w), fmaf(g_d2, wb.x, pb.x + qb.x), fmaf(g_d2, wb.y, pb.y + qb.y),
+                                        fmaf(g_d2, wb.z, pb.z + qb.z), fmaf(g_d2, wb.w, pb.w + qb.w)};
+                    uint32_t hw[4], lw[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) split_bf16x2(silu_fast(x[2 * e]), silu_fast(x[2 * e + 1]), hw[e], lw[e]);
+                    *reinterpret_cast<uint4*>(a_hi + a_row_off + k8 * 128) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                    *reinterpret_cast<uint4*>(a_hi + A_PART + a_row_off + k8 * 128) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&a_full[st]);
+            }
+            // sQ / sD2 of this tile are read only by the generators themselves: all of them must be past the tile's last
+            // chunk before the next tile's setup overwrites them
+            named_bar_sync(1, GEN_THREADS);
+        }
+    } else {
+        // ---------------------------------------------------------------- epilogue warps 9..16
+        const int ew = warp - (TC2_GEN_WARPS + 1);       // 0..7
+        const int quad = warp & 3;                        // TMEM lane quadrant this warp may access (= warp id % 4)
+        const int half = ew >> 2;                         // channel half handled by this warp: ew = {quadrant order} x half
+        const int e_row = quad * 32 + lane;
+        const int e_il = e_row >> 4;
+        const bool b3 = (lane & 8) != 0, b2 = (lane & 4) != 0, b1 = (lane & 2) != 0, b0 = (lane & 1) != 0;
+        for (int t = 0; t < n_tiles; ++t) {
+            const uint32_t buf = uint32_t(t) & 1u;
+            const float* sValidT = (t & 1) ? (fl + TC2F_VALID2) : (fl + TCF_VALID);
+            mbar_wait(&tmem_full[buf], (uint32_t(t) >> 1) & 1u);
+            tcg_fence_after();
+            const uint32_t tbase = tmem_base + (uint32_t(quad * 32) << 16) + buf * uint32_t(EM) + uint32_t(half * 128);
+            // ---- pass A: gate dot product over this thread's 128 channels
+            float gd = 0.f;
+#pragma unroll 1
+            for (int part = 0; part < 4; ++part) {
+                uint32_t r[32];
+                tcg_ld32(tbase + uint32_t(part * 32), r);
+                tcg_wait_ld();
+#pragma unroll
+                for (int e = 0; e < 32; ++e) {
+                    const int ch = half * 128 + part * 32 + e;
+                    gd = fmaf(silu_fast(__uint_as_float(r[e]) + sB2[ch]), sWg[ch], gd);
+                }
+            }
+            sGp[half * TP + e_row] = gd;
+            named_bar_sync(2, TC2_EPI_WARPS * 32);
+            const float gate = sigmoid_fast((sGp[e_row] + sGp[TP + e_row]) + p.bg) * sValidT[e_row];
+            // ---- pass B: recompute SiLU, apply the gate, sum over the 16 residues j (16 lanes) 32 channels at a time
+#pragma unroll 1
+            for (int part = 0; part < 4; ++part) {
+                uint32_t r[32];
+                tcg_ld32(tbase + uint32_t(part * 32), r);
+                tcg_wait_ld();
+                float v[32], t16[16], t8[8], t4[4], t2[2];
+#pragma unroll
+                for (int e = 0; e < 32; ++e) v[e] = silu_fast(__uint_as_float(r[e]) + sB2[half * 128 + part * 32 + e]) * gate;
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    const float keep = b3 ? v[k + 16] : v[k], send = b3 ? v[k] : v[k + 16];
+                    t16[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const float keep = b2 ? t16[k + 8] : t16[k], send = b2 ? t16[k] : t16[k + 8];
+                    t8[k] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float keep = b1 ? t8[k + 4] : t8[k], send = b1 ? t8[k] : t8[k + 4];
+                    t4[k] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+                }
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    const float keep = b0 ? t4[k + 2] : t4[k], send = b0 ? t4[k] : t4[k + 2];
+                    t2[k] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+                }
+                // this lane owns 2 channels of residue e_il for this part: unique owner of (residue i, channel) in the CTA
+                const int ch0 = half * 128 + part * 32 + (b3 ? 16 : 0) + (b2 ? 8 : 0) + (b1 ? 4 : 0) + (b0 ? 2 : 0);
+                sMsum[e_il * EM + ch0] += t2[0];
+                sMsum[e_il * EM + ch0 + 1] += t2[1];
+            }
+            // buffer drained (and sGp / this parity's validity mask no longer needed): hand it back
+            tcg_fence_before();
+            named_bar_sync(2, TC2_EPI_WARPS * 32);  // every epilogue warp has read sGp before the next tile rewrites it
+            if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+        }
+    }
+
+    tcg_fence_before();
+    __syncthreads();
+    for (int e = tid; e < TI * EM; e += TC2_THREADS) {
+        const int il = e / EM, c = e % EM;
+        if (i0 + il < L) p.M[size_t(start + i0 + il) * EM + c] = sMsum[e];
+    }
+    if (warp == 0) {
+        tcg_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ K_e3
 // f'[r] = W4 SiLU(W3 [f_r, m_r] + b3) + b4 + f_r      (node_mlp + residual, my_egnn_nocoords.py:71-72)
 constexpr int NM_ROWS = 16;
+// (input and hidden tiles are stored transposed, [k][16 residues], and read with LDS.128)
 __global__ void __launch_bounds__(256) embed_node_mlp_kernel(const float* __restrict__ feats, const float* __restrict__ M, int n_res,
                                                              const float* __restrict__ w3t /*[384][256]*/, const float* __restrict__ b3,
                                                              const float* __restrict__ w4t /*[256][128]*/, const float* __restrict__ b4,
                                                              float* __restrict__ feats_out) {
-    __shared__ float sIn[NM_ROWS][EW + EM];
-    __shared__ float sN1[NM_ROWS][EM];
+    __shared__ __align__(16) float sInT[EW + EM][NM_ROWS];
+    __shared__ __align__(16) float sN1T[EM][NM_ROWS];
     const int r0 = blockIdx.x * NM_ROWS, tid = threadIdx.x;
     for (int e = tid; e < NM_ROWS * (EW + EM); e += 256) {
         const int r = e / (EW + EM), k = e % (EW + EM);
         float v = 0.f;
         if (r0 + r < n_res) v = (k < EW) ? feats[size_t(r0 + r) * EW + k] : M[size_t(r0 + r) * EM + (k - EW)];
-        sIn[r][k] = v;
+        sInT[k][r] = v;
     }
     __syncthreads();
     {
@@ -680,11 +966,18 @@ __global__ void __launch_bounds__(256) embed_node_mlp_kernel(const float* __rest
 #pragma unroll 4
         for (int k = 0; k < EW + EM; ++k) {
             const float w = w3t[size_t(k) * EM + c];
+            const float4* f4 = reinterpret_cast<const float4*>(&sInT[k][0]);
 #pragma unroll
-            for (int r = 0; r < NM_ROWS; ++r) acc[r] = fmaf(sIn[r][k], w, acc[r]);
+            for (int r4 = 0; r4 < NM_ROWS / 4; ++r4) {
+                const float4 f = f4[r4];
+                acc[4 * r4 + 0] = fmaf(f.x, w, acc[4 * r4 + 0]);
+                acc[4 * r4 + 1] = fmaf(f.y, w, acc[4 * r4 + 1]);
+                acc[4 * r4 + 2] = fmaf(f.z, w, acc[4 * r4 + 2]);
+                acc[4 * r4 + 3] = fmaf(f.w, w, acc[4 * r4 + 3]);
+            }
         }
 #pragma unroll
-        for (int r = 0; r < NM_ROWS; ++r) sN1[r][c] = silu(acc[r]);
+        for (int r = 0; r < NM_ROWS; ++r) sN1T[c][r] = silu(acc[r]);
     }
     __syncthreads();
     {
@@ -696,13 +989,20 @@ __global__ void __launch_bounds__(256) embed_node_mlp_kernel(const float* __rest
 #pragma unroll 4
         for (int k = 0; k < EM; ++k) {
             const float w = w4t[size_t(k) * EW + c];
+            const float4* f4 = reinterpret_cast<const float4*>(&sN1T[k][half * (NM_ROWS / 2)]);
 #pragma unroll
-            for (int r = 0; r < NM_ROWS / 2; ++r) acc[r] = fmaf(sN1[half * (NM_ROWS / 2) + r][k], w, acc[r]);
+            for (int r4 = 0; r4 < NM_ROWS / 8; ++r4) {
+                const float4 f = f4[r4];
+                acc[4 * r4 + 0] = fmaf(f.x, w, acc[4 * r4 + 0]);
+                acc[4 * r4 + 1] = fmaf(f.y, w, acc[4 * r4 + 1]);
+                acc[4 * r4 + 2] = fmaf(f.z, w, acc[4 * r4 + 2]);
+                acc[4 * r4 + 3] = fmaf(f.w, w, acc[4 * r4 + 3]);
+            }
         }
 #pragma unroll
         for (int r = 0; r < NM_ROWS / 2; ++r) {
             const int rr = half * (NM_ROWS / 2) + r;
-            if (r0 + rr < n_res) feats_out[size_t(r0 + rr) * EW + c] = acc[r] + sIn[rr][c];
+            if (r0 + rr < n_res) feats_out[size_t(r0 + rr) * EW + c] = acc[r] + sInT[c][rr];
         }
     }
 }
@@ -760,7 +1060,7 @@ struct fcs_embedder {
     int *s_start = nullptr, *s_len = nullptr;
     int2* items = nullptr;
     fcs_embed_timing timing = {};
-    int mode = FCS_EMBED_MODE_TC;  // which edge kernel runs (fcs_embed_set_mode; FCS_EMBED_MODE env var at create time)
+    int mode = FCS_EMBED_MODE_TC3;  // which edge kernel runs (fcs_embed_set_mode; FCS_EMBED_MODE env var at create time)
 };
 
 namespace {
@@ -923,7 +1223,11 @@ int run_pass(fcs_embedder* e, const float* coords, const int64_t* offsets, int s
         ep.w2img = w.w2img;
         const bool timed = *edge_events < fcs_embedder::MAX_EDGE_EVENTS;
         if (timed) EMB_CUDA(cudaEventRecord(e->edge_ev[2 * *edge_events], st));
-        if (e->mode == FCS_EMBED_MODE_TC)
+        if (e->mode == FCS_EMBED_MODE_TC2)
+            embed_edge_tc2_kernel<8><<<int(n_items), tc2_threads(8), EDGE_TC2_SMEM, st>>>(ep);
+        else if (e->mode == FCS_EMBED_MODE_TC3)
+            embed_edge_tc2_kernel<16><<<int(n_items), tc2_threads(16), EDGE_TC2_SMEM, st>>>(ep);
+        else if (e->mode == FCS_EMBED_MODE_TC)
             embed_edge_tc_kernel<<<int(n_items), TC_THREADS_ALL, EDGE_TC_SMEM, st>>>(ep);
         else
             embed_edge_kernel<<<int(n_items), EDGE_THREADS, EDGE_SMEM, st>>>(ep);
@@ -1035,7 +1339,12 @@ extern "C" int fcs_embedder_create(int device, const fcs_egnn_weights* layers, i
         e->sm_count = prop.multiProcessorCount;
         EMB_CUDA(cudaFuncSetAttribute(embed_edge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, EDGE_SMEM));
         EMB_CUDA(cudaFuncSetAttribute(embed_edge_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, EDGE_TC_SMEM));
-        if (const char* m = getenv("FCS_EMBED_MODE")) e->mode = (atoi(m) == FCS_EMBED_MODE_FP32) ? FCS_EMBED_MODE_FP32 : FCS_EMBED_MODE_TC;
+        EMB_CUDA(cudaFuncSetAttribute(embed_edge_tc2_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, EDGE_TC2_SMEM));
+        EMB_CUDA(cudaFuncSetAttribute(embed_edge_tc2_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, EDGE_TC2_SMEM));
+        if (const char* m = getenv("FCS_EMBED_MODE")) {
+            const int v = atoi(m);
+            if (v >= FCS_EMBED_MODE_FP32 && v <= FCS_EMBED_MODE_TC3) e->mode = v;
+        }
         EMB_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
         EMB_CUDA(cudaEventCreate(&e->ev0));
         EMB_CUDA(cudaEventCreate(&e->ev1));
@@ -1086,7 +1395,7 @@ extern "C" int fcs_embed_to_device(fcs_embedder* e, const float* coords, const i
 
 extern "C" int fcs_embed_set_mode(fcs_embedder* e, int mode) {
     if (!e) return efail(FCS_ERR_INVALID, "fcs_embed_set_mode: null embedder");
-    if (mode != FCS_EMBED_MODE_FP32 && mode != FCS_EMBED_MODE_TC) return efail(FCS_ERR_INVALID, "fcs_embed_set_mode: unknown mode %d", mode);
+    if (mode < FCS_EMBED_MODE_FP32 || mode > FCS_EMBED_MODE_TC3) return efail(FCS_ERR_INVALID, "fcs_embed_set_mode: unknown mode %d", mode);
     e->mode = mode;
     return FCS_OK;
 }

@@ -21,7 +21,7 @@ OK, ERR_INVALID, ERR_CUDA, ERR_STATE, ERR_UNSUPPORTED, ERR_NOMEM = 0, -1, -2, -3
 DB_NORMALISE_ROWS, DB_KEEP_BF16, DB_HAS_LENGTHS = 1, 2, 4
 QNORM_NONE, QNORM_COSINE, QNORM_L2 = 0, 1, 2
 MODE_AUTO, MODE_GEMV, MODE_TC = 0, 1, 2
-EMBED_MODE_FP32, EMBED_MODE_TC = 0, 1
+EMBED_MODE_FP32, EMBED_MODE_TC, EMBED_MODE_TC2, EMBED_MODE_TC3 = 0, 1, 2, 3
 
 EXPORTS = [
     "fcs_version", "fcs_last_error", "fcs_device_count", "fcs_db_create", "fcs_db_upload",
@@ -443,7 +443,8 @@ class Embedder:
         return feats, msgs
 
     def set_mode(self, mode: int) -> None:
-        """EMBED_MODE_FP32 (fp32 FMA pipe) or EMBED_MODE_TC (tcgen05, bf16 hi/lo split)."""
+        """EMBED_MODE_FP32 (fp32 FMA pipe), EMBED_MODE_TC (round-1 tcgen05 kernel), EMBED_MODE_TC2 / EMBED_MODE_TC3 (tcgen05 with
+        dedicated epilogue warps and two accumulator buffers, 8 / 16 generator warps; TC3 is the library's default)."""
         _check(self._lib.fcs_embed_set_mode(self._h, int(mode)))
 
     def timing(self) -> EmbedTiming:

@@ -21,13 +21,15 @@ def golden():
     return load_golden()
 
 
-@pytest.fixture(scope="module", params=["tc", "fp32"])
+@pytest.fixture(scope="module", params=["tc3", "tc2", "tc", "fp32"])
 def embedder(golden, request):
-    """Both edge kernels behind the same ABI: tcgen05 (bf16 hi/lo split, the default) and the fp32 FMA-pipe kernel."""
+    """All edge kernels behind the same ABI: the three tcgen05 kernels (bf16 hi/lo split; tc3 is the default) and the fp32
+    FMA-pipe kernel."""
     _, sd, _ = golden
     e = b200_embed.FoldClassEmbedder(sd, device=0)
     assert e._emb.timing().last_launches == 0
-    e._emb.set_mode(native.EMBED_MODE_TC if request.param == "tc" else native.EMBED_MODE_FP32)
+    e._emb.set_mode({"tc3": native.EMBED_MODE_TC3, "tc2": native.EMBED_MODE_TC2, "tc": native.EMBED_MODE_TC,
+                     "fp32": native.EMBED_MODE_FP32}[request.param])
     yield e
     e.close()
 
