@@ -75,3 +75,38 @@ def test_synthetic_database_is_one_global_block_matrix():
         assert all(a[1] == b[0] for a, b in zip(seen, seen[1:]))
     ids = bench.planted_ids(rows_total)
     assert len(ids) == bench.PLANTED and len({i * 8 // rows_total for i in ids}) == 8  # one planted row in every eighth
+
+
+def test_the_in_bench_parity_check_catches_wrong_results():
+    """bench.parity_check is what lets the driver's N-GPU lines carry correctness: exercise the checker itself on CPU
+    tensors -- a correct result passes, a wrong id, a wrong score and a lost planted row fail."""
+    sys.path.insert(0, ROOT)
+    import numpy as np
+    import torch
+
+    import bench
+    from merizo_search_b200 import synth
+
+    dev, blk, rows_total, nq, k = torch.device("cpu"), 4096, 20_000, 32, 10
+    wl = {"mask": False}
+    q = torch.nn.functional.normalize(torch.randn((nq, 128), generator=torch.Generator().manual_seed(1)))
+    planted = bench.plant_queries(q, rows_total, dev, synth, blk, 1000)
+    assert planted == bench.planted_ids(rows_total)
+    db = torch.cat([synth.device_block(gb, n, dev, base_seed=1000)[lo:hi] for gb, n, lo, hi in bench.shard_blocks(0, rows_total, rows_total, blk)])
+    sc, ids = torch.topk(q @ db.T, k, dim=1)
+
+    def check(sc_, ids_):
+        return bench.parity_check(sc_, ids_, q, k, wl, rows_total, 0, rows_total, None, dev, synth, blk, 1000, 1, None, torch)
+
+    good = check(sc, ids)
+    assert good["ok"] and good["planted_queries"] == bench.PLANTED and good["brute_force_queries"] >= 4, good
+    assert [int(ids[j, 0]) for j in range(bench.PLANTED)] == planted
+    bad_ids = ids.clone()
+    bad_ids[0, 3] = (bad_ids[0, 3] + 1) % rows_total          # a wrong row at rank 3 of a sampled query
+    bad_sc = sc.clone()
+    bad_sc[nq - 1, 0] += 1e-3                                  # a wrong score
+    lost = ids.clone()
+    lost[5, 0] = lost[5, 1]                                    # planted query 5 no longer returns its row first
+    res_ids, res_sc, res_lost = check(sc, bad_ids), check(bad_sc, ids), check(sc, lost)
+    assert not res_sc["ok"] and not res_lost["ok"], (res_sc, res_lost)
+    assert not res_ids["ok"] and res_ids["id_mismatches_beyond_ties"] == 1, res_ids  # right score, wrong row: not a tie
